@@ -1,0 +1,168 @@
+/*
+ * iblb200.h -- C ABI of the B200-native OpenIBL hot path (libiblb200.so).
+ *
+ * Drop-in boundary for the one data-parallel path of yxgeee/OpenIBL:
+ *   VGG16 conv1_1..conv5_3 -> NetVLAD (+intra-norm, L2) -> PCA-whiten + L2
+ *   -> query x database L2 distance -> top-k.
+ * The reference is pure Python on torch ops and has no FFI of its own; each
+ * entry point below names the reference call site (file:line under the
+ * reference root) whose arithmetic it replaces.  The host-side mirror of the
+ * reference API (ibl.models / ibl.evaluators / ibl.pca) binds these symbols with
+ * ctypes -- see INTEGRATION.md for the stub a reference maintainer would add.
+ *
+ * Conventions
+ *   - extern "C", plain pointers and sizes; no torch / C++ types.
+ *   - Every function returns an ibl_status (0 = OK) and never throws.
+ *   - Unless a name ends in _host, pointers are DEVICE pointers on the engine's
+ *     device; fp32, contiguous.  `stream` is a cudaStream_t passed as void*
+ *     (NULL = legacy default stream).  No hidden synchronisation except in the
+ *     *_host entry points, which return after their result is in host memory.
+ *   - The caller owns every input and output buffer.  The engine owns only its
+ *     workspace and re-laid-out weight copies.
+ *   - One engine per (process, GPU); not thread-safe (the reference drives one
+ *     GPU from one Python thread, scripts/test_dist.sh:27).
+ */
+#ifndef IBLB200_H_
+#define IBLB200_H_
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define IBLB200_ABI_VERSION 1
+
+typedef enum ibl_status {
+  IBL_OK = 0,
+  IBL_ERR_BAD_ARG = 1,       /* null pointer, non-positive size, unsupported shape */
+  IBL_ERR_NOT_READY = 2,     /* weights for the requested stage were never set */
+  IBL_ERR_CUDA = 3,          /* a CUDA runtime/driver call failed (see ibl_last_error) */
+  IBL_ERR_NO_DEVICE = 4,     /* no usable sm_100 device: there is NO CPU fallback */
+  IBL_ERR_OOM = 5,           /* workspace allocation failed */
+  IBL_ERR_UNSUPPORTED = 6    /* valid request this build cannot serve */
+} ibl_status;
+
+typedef struct ibl_engine ibl_engine;
+
+/* extraction flags for ibl_extract / ibl_extract_host */
+#define IBL_OUT_VLAD 0x1u  /* out = L2(flatten(intra-norm(vlad)))  [N, K*C]   (EmbedNet, netvlad.py:73-82) */
+#define IBL_OUT_PCA  0x2u  /* out = L2(W out_vlad + b)              [N, P]     (EmbedNetPCA, netvlad.py:95-110) */
+#define IBL_OUT_POOL 0x4u  /* also write pool [N,512]               (vgg.py:67-70) */
+
+/* conv math mode (ibl_engine_set_conv_mode) */
+#define IBL_CONV_SIMT_FP32 0  /* fp32 CUDA-core implicit GEMM (verification path)              */
+#define IBL_CONV_TC_BF16X3 1  /* tcgen05 implicit GEMM, bf16 hi/lo split, 3 MMAs, fp32 accum   */
+
+int ibl_abi_version(void);
+const char* ibl_status_string(int status);
+/* Text of the most recent failure on this thread ("" if none). */
+const char* ibl_last_error(void);
+
+/* ---- engine lifetime ------------------------------------------------------- */
+int ibl_engine_create(int device, ibl_engine** out);
+int ibl_engine_destroy(ibl_engine* e);
+int ibl_engine_set_conv_mode(ibl_engine* e, int mode);
+int ibl_engine_get_conv_mode(ibl_engine* e, int* mode);
+/* Number of kernels this library has launched through `e` since creation. */
+int ibl_engine_launch_count(ibl_engine* e, uint64_t* count);
+
+/* ---- parameters ------------------------------------------------------------ */
+/* VGG16 trunk parameters, reference layout: weights[i] is OIHW [Cout,Cin,3,3],
+ * biases[i] is [Cout], i = conv1_1..conv5_3 (state-dict slots
+ * base.{0,2,5,7,10,12,14,17,19,21,24,26,28}, vgg.py:40-42).  The engine keeps
+ * re-laid-out copies; call again after the parameters change. */
+int ibl_engine_set_vgg16(ibl_engine* e, const float* const* weights13,
+                         const float* const* biases13, void* stream);
+/* NetVLAD parameters: conv_w [K,C] (net_vlad.conv.weight squeezed), centroids [K,C]
+ * (netvlad.py:28-29). */
+int ibl_engine_set_netvlad(ibl_engine* e, const float* conv_w, const float* centroids,
+                           int K, int C, void* stream);
+/* PCA-whitening layer: W [P,D] (pca_layer.weight squeezed == PCA.load weight,
+ * pca.py:105), b [P]. */
+int ibl_engine_set_pca(ibl_engine* e, const float* W, const float* b, int P, int D, void* stream);
+
+/* ---- stage (i): backbone --------------------------------------------------- */
+/* VGG.forward -> self.base (vgg.py:61-62) and gap (vgg.py:67-70).
+ * x NCHW [N,3,H,W]  ->  feat_nhwc [N,H/16,W/16,512] (engine-native layout, may be NULL),
+ * feat_nchw [N,512,H/16,W/16] (reference layout, may be NULL), pool [N,512] (may be NULL). */
+int ibl_vgg16_forward(ibl_engine* e, const float* x_nchw, int N, int H, int W,
+                      float* feat_nhwc, float* feat_nchw, float* pool, void* stream);
+
+/* ---- stage (ii): NetVLAD --------------------------------------------------- */
+/* NetVLAD.forward (netvlad.py:44-61) + EmbedNet normalisation (netvlad.py:78-80), fused.
+ * feat is [N,S,C] if nhwc != 0 else [N,C,S].  conv_w/centroids [K,C] are read directly.
+ * vlad_raw [N,K,C] (un-normalised, what NetVLAD.forward returns; may be NULL)
+ * vlad_norm [N,K*C] (intra-norm + flatten + L2; may be NULL). */
+int ibl_netvlad_forward(ibl_engine* e, const float* feat, int nhwc, int N, int C, int S,
+                        const float* conv_w, const float* centroids, int K,
+                        int normalize_input, float* vlad_raw, float* vlad_norm, void* stream);
+/* Only the two normalisations (netvlad.py:78-80): vlad_raw [N,K,C] -> out [N,K*C]. */
+int ibl_vlad_normalize(ibl_engine* e, const float* vlad_raw, int N, int K, int C,
+                       float* out, void* stream);
+
+/* ---- stage (iii-a): PCA-whiten + L2 ---------------------------------------- */
+/* EmbedNetPCA.pca_layer + F.normalize (netvlad.py:105-108) == PCA.infer (pca.py:108-123).
+ * v [N,D], W [P,D], b [P] -> out [N,P]. */
+int ibl_pca_l2(ibl_engine* e, const float* v, int N, int D, const float* W, const float* b,
+               int P, float* out, void* stream);
+/* F.normalize(x, p=2, dim=-1) (evaluators.py:29-33): rows [N,D] in place or to out. */
+int ibl_l2_normalize_rows(ibl_engine* e, const float* x, int N, int D, float* out, void* stream);
+
+/* ---- whole extraction ------------------------------------------------------ */
+/* extract_cnn_feature + pca (evaluators.py:22-34,56-57) with parameters set on the engine.
+ * out is [N,K*C] for IBL_OUT_VLAD, [N,P] for IBL_OUT_VLAD|IBL_OUT_PCA; pool [N,512] if
+ * IBL_OUT_POOL. */
+int ibl_extract(ibl_engine* e, const float* x_nchw, int N, int H, int W, unsigned flags,
+                float* out, float* pool, void* stream);
+/* Same through HOST buffers (pinned or pageable): H2D of x, the pipeline, D2H of out (+pool),
+ * then a stream synchronise -- the reference's per-batch `.cuda()` ... `.cpu()`
+ * (evaluators.py:24,58). */
+int ibl_extract_host(ibl_engine* e, const float* x_nchw_host, int N, int H, int W,
+                     unsigned flags, float* out_host, float* pool_host, void* stream);
+
+/* ---- stage (iii-b): distance + ranking ------------------------------------- */
+/* pairwise_distance (evaluators.py:127-129): out[i,j] = |q_i|^2 + |db_j|^2 - 2 q_i.db_j,
+ * q [m,d], db [n,d], out [m,n].  Kept for the callers that need the dense matrix
+ * (netvlad_img.py:78). */
+int ibl_l2dist_dense(ibl_engine* e, const float* q, int m, const float* db, int n, int d,
+                     float* out, void* stream);
+/* Fused distance + per-query top-k over one database shard; replaces pairwise_distance +
+ * np.argsort (evaluators.py:127-129,143) for the ranks evaluate_all reads (:151-159).
+ * out_dist [m,k] ascending, out_idx [m,k] = idx_base + row in db; ties: lowest index first.
+ * n_valid <= n rows of db are real (the rest is DistributedSliceSampler padding,
+ * sampler.py:208-219, and is ignored).  k <= 128. */
+int ibl_l2dist_topk(ibl_engine* e, const float* q, int m, const float* db, int n, int n_valid,
+                    int d, int k, int64_t idx_base, float* out_dist, int64_t* out_idx,
+                    void* stream);
+/* Per-row top-k of an existing dense matrix dist [m,n] (row stride n): the ranks evaluate_all reads
+ * from np.argsort (evaluators.py:143,151-159).  Same ordering rule as ibl_l2dist_topk. */
+int ibl_topk_rows(ibl_engine* e, const float* dist, int m, int n, int k, float* out_dist,
+                  int64_t* out_idx, void* stream);
+/* k-way merge of per-shard candidates (after the NCCL all-gather): cand_* [parts,m,k_in]
+ * -> out_* [m,k_out] ascending by (dist, idx). Entries with idx < 0 are ignored. */
+int ibl_topk_merge(ibl_engine* e, const float* cand_dist, const int64_t* cand_idx, int parts,
+                   int m, int k_in, int k_out, float* out_dist, int64_t* out_idx, void* stream);
+/* Host-buffer variant of ibl_l2dist_topk for the e2e measurement: H2D of q and db, kernel,
+ * D2H of results, synchronise. */
+int ibl_l2dist_topk_host(ibl_engine* e, const float* q_host, int m, const float* db_host, int n,
+                         int d, int k, float* out_dist_host, int64_t* out_idx_host, void* stream);
+
+/* ---- self-tests (GPU) ------------------------------------------------------ */
+/* Runs the tcgen05/TMA building blocks against CUDA-core results on the device;
+ * returns IBL_OK when all agree. max_rel_err (may be NULL) receives the worst error. */
+int ibl_selftest_tc(ibl_engine* e, float* max_rel_err);
+
+/* One 3x3/s1/p1 conv layer in isolation (test hook): x NHWC [N,H,W,Cin] fp32, w OIHW, optional
+ * ReLU and fused 2x2 max-pool, y NHWC fp32.  mode: IBL_CONV_SIMT_FP32, IBL_CONV_TC_BF16X3 (fp32
+ * epilogue) or 2 (tcgen05 with the bf16 hi/lo plane epilogue, converted back to fp32).
+ * bn_override forces the N tile (64/128/256) when it divides Cout, 0 = default. Synchronises. */
+int ibl_debug_conv3x3(ibl_engine* e, const float* x_nhwc, int N, int H, int W, int cin,
+                      const float* w_oihw, const float* bias, int cout, int relu, int pool, int mode,
+                      int bn_override, float* y_nhwc, void* stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* IBLB200_H_ */

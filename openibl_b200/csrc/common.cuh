@@ -1,0 +1,111 @@
+// Shared declarations for libiblb200 (sm_100a only).
+#pragma once
+#include <cuda_runtime.h>
+#include <cuda_bf16.h>
+#include <stdint.h>
+#include <stdio.h>
+#include <string>
+
+#include "../../include/iblb200.h"
+
+namespace ibl {
+
+void set_last_error(const std::string& s);
+
+#define IBL_CUDA_OK(expr)                                                          \
+  do {                                                                             \
+    cudaError_t _e = (expr);                                                       \
+    if (_e != cudaSuccess) {                                                       \
+      ::ibl::set_last_error(std::string(#expr) + ": " + cudaGetErrorString(_e) +   \
+                            " (" __FILE__ ":" + std::to_string(__LINE__) + ")");   \
+      return IBL_ERR_CUDA;                                                         \
+    }                                                                              \
+  } while (0)
+
+#define IBL_RET(expr)                 \
+  do {                                \
+    int _s = (expr);                  \
+    if (_s != IBL_OK) return _s;      \
+  } while (0)
+
+#define IBL_REQUIRE(cond, msg)                                  \
+  do {                                                          \
+    if (!(cond)) {                                              \
+      ::ibl::set_last_error(std::string("bad argument: ") + msg); \
+      return IBL_ERR_BAD_ARG;                                   \
+    }                                                           \
+  } while (0)
+
+static inline int cdiv(long long a, long long b) { return (int)((a + b - 1) / b); }
+
+// One conv layer of the VGG16 trunk.
+struct ConvLayer {
+  int cin, cout;
+  bool relu;       // ReLU after the conv (all but conv5_3, vgg.py:41-42)
+  bool pool;       // MaxPool2x2 after the ReLU (blocks 1-4)
+};
+
+// Device-side parameter store of one conv layer.
+struct ConvParams {
+  float* w_tck = nullptr;            // SIMT layout  [9][Cin][Cout] fp32
+  float* bias = nullptr;             // [Cout]
+  __nv_bfloat16* w_hi = nullptr;     // TC layout    [9][Cout][Cin_pad] bf16 (hi part)
+  __nv_bfloat16* w_lo = nullptr;     //                                      (lo part)
+  int cin_pad = 0;
+};
+
+// ---- launchers implemented in the .cu files ------------------------------------------------
+// simt_conv.cu
+int launch_repack_weights(const float* w_oihw, int cout, int cin, ConvParams& p, cudaStream_t s);
+int launch_conv3x3_simt(const float* x_nhwc, const ConvParams& p, int N, int H, int W, int cin,
+                        int cout, bool relu, float* y_nhwc, cudaStream_t s);
+int launch_conv1_1(const float* x_nchw, const ConvParams& p, int N, int H, int W, bool to_planes,
+                   float* y_nhwc, __nv_bfloat16* y_hi, __nv_bfloat16* y_lo, cudaStream_t s);
+int launch_maxpool2x2(const float* x, int N, int H, int W, int C, float* y, cudaStream_t s);
+int launch_nhwc_to_nchw(const float* x, int N, int S, int C, float* y, cudaStream_t s);
+int launch_global_maxpool_nhwc(const float* x, int N, int S, int C, float* y, cudaStream_t s);
+int launch_planes_to_f32(const __nv_bfloat16* hi, const __nv_bfloat16* lo, size_t n, float* y,
+                         cudaStream_t s);
+int launch_f32_to_planes(const float* x, size_t n, __nv_bfloat16* hi, __nv_bfloat16* lo,
+                         cudaStream_t s);
+
+// tc_conv.cu  (tcgen05 + TMA implicit GEMM, bf16 hi/lo split operands)
+struct TcConvPlan;   // opaque per-engine cache of TMA descriptors
+int tc_driver_init();   // resolves cuTensorMapEncodeTiled; IBL_ERR_NO_DEVICE if unavailable
+int launch_conv3x3_tc(const __nv_bfloat16* x_hi, const __nv_bfloat16* x_lo, const ConvParams& p,
+                      int N, int H, int W, int cin, int cout, bool relu, bool pool,
+                      __nv_bfloat16* y_hi, __nv_bfloat16* y_lo, float* y_f32, cudaStream_t s);
+int launch_maxpool2x2_planes(const __nv_bfloat16* hi, const __nv_bfloat16* lo, int N, int H, int W,
+                             int C, __nv_bfloat16* yhi, __nv_bfloat16* ylo, cudaStream_t s);
+int tc_selftest(float* max_rel_err, cudaStream_t s);
+
+// netvlad.cu
+struct NetvladWorkspace {
+  float* assign = nullptr;   // [N,S,K]  soft-assignment * inv-norm handled in kernel
+  float* invnorm = nullptr;  // [N,S]
+  float* asum = nullptr;     // [N,K]
+  float* raw = nullptr;      // [N,K,C]  (used when the caller does not want vlad_raw)
+  size_t cap_N = 0;
+  int cap_S = 0, cap_K = 0, cap_C = 0;
+};
+int launch_netvlad(const float* feat, bool nhwc, int N, int C, int S, const float* conv_w,
+                   const float* centroids, int K, bool normalize_input, float* assign,
+                   float* invnorm, float* asum, float* vlad_raw, float* vlad_norm,
+                   cudaStream_t s, uint64_t* launches);
+int launch_vlad_normalize(const float* raw, int N, int K, int C, float* out, cudaStream_t s);
+
+// gemm_simt.cu  (C = A[m,K] . B[n,K]^T family)
+int launch_pca_l2(const float* v, int N, int D, const float* W, const float* b, int P,
+                  float* partial, int splits, float* out, cudaStream_t s, uint64_t* launches);
+int launch_l2_normalize_rows(const float* x, int N, int D, float* out, cudaStream_t s);
+int launch_row_sqnorm(const float* x, int N, int D, float* out, cudaStream_t s);
+int launch_l2dist_dense(const float* q, const float* qn, int m, const float* db, const float* dbn,
+                        int n, int d, float* out, long long ld_out, cudaStream_t s);
+
+// topk.cu
+int launch_topk_rows(const float* dist, long long ld, int m, int n_valid, int k, int64_t idx_base,
+                     float* out_dist, int64_t* out_idx, bool accumulate, cudaStream_t s);
+int launch_topk_merge(const float* cand_dist, const int64_t* cand_idx, int parts, int m, int k_in,
+                      int k_out, float* out_dist, int64_t* out_idx, cudaStream_t s);
+
+}  // namespace ibl

@@ -1,0 +1,563 @@
+// C-ABI entry points of libiblb200 (see include/iblb200.h).  The engine owns the workspace
+// arena and the re-laid-out weights; every entry point validates its arguments, enqueues
+// kernels on the caller's stream and returns a status code -- it never throws and never
+// synchronises, except for the *_host variants.
+#include <mutex>
+#include <new>
+#include <vector>
+
+#include "common.cuh"
+
+namespace ibl {
+
+static thread_local std::string g_last_error;
+void set_last_error(const std::string& s) { g_last_error = s; }
+void tc_set_bn_override(int bn);
+
+static const ConvLayer kVgg16[13] = {
+    {3, 64, true, false},    {64, 64, true, true},     // block 1
+    {64, 128, true, false},  {128, 128, true, true},   // block 2
+    {128, 256, true, false}, {256, 256, true, false}, {256, 256, true, true},   // block 3
+    {256, 512, true, false}, {512, 512, true, false}, {512, 512, true, true},   // block 4
+    {512, 512, true, false}, {512, 512, true, false}, {512, 512, false, false}  // block 5 (no ReLU last)
+};
+
+// A growable device buffer.
+struct DevBuf {
+  void* p = nullptr;
+  size_t cap = 0;
+  int ensure(size_t bytes) {
+    if (bytes <= cap) return IBL_OK;
+    if (p) cudaFree(p);
+    p = nullptr;
+    cap = 0;
+    cudaError_t e = cudaMalloc(&p, bytes);
+    if (e != cudaSuccess) {
+      cudaGetLastError();
+      set_last_error("workspace cudaMalloc(" + std::to_string(bytes) + " B) failed: " + cudaGetErrorString(e));
+      return IBL_ERR_OOM;
+    }
+    cap = bytes;
+    return IBL_OK;
+  }
+  void release() {
+    if (p) cudaFree(p);
+    p = nullptr;
+    cap = 0;
+  }
+  template <class T> T* as() const { return reinterpret_cast<T*>(p); }
+};
+
+}  // namespace ibl
+
+using namespace ibl;
+
+struct ibl_engine {
+  int device = 0;
+  int conv_mode = IBL_CONV_TC_BF16X3;
+  uint64_t launches = 0;
+  bool vgg_ready = false;
+  ConvParams conv[13];
+  // borrowed NetVLAD / PCA parameters (owned by the caller's torch Parameters)
+  const float* nv_w = nullptr;
+  const float* nv_c = nullptr;
+  int nv_K = 0, nv_C = 0;
+  const float* pca_W = nullptr;
+  const float* pca_b = nullptr;
+  int pca_P = 0, pca_D = 0;
+  // workspace
+  DevBuf act[2];       // activation ping-pong (fp32 NHWC, or bf16 hi|lo planes back to back)
+  DevBuf feat;         // conv5_3 output, fp32 NHWC
+  DevBuf nv_assign, nv_inv, nv_raw, vlad;
+  DevBuf pca_partial;
+  DevBuf qn, dbn, dist_chunk, cand_d, cand_i;
+  DevBuf stage_in, stage_out, stage_out2;
+};
+
+namespace {
+
+inline cudaStream_t S(void* s) { return reinterpret_cast<cudaStream_t>(s); }
+
+struct DeviceGuard {
+  int prev = -1;
+  explicit DeviceGuard(int dev) {
+    cudaGetDevice(&prev);
+    if (prev != dev) cudaSetDevice(dev);
+    else prev = -1;
+  }
+  ~DeviceGuard() {
+    if (prev >= 0) cudaSetDevice(prev);
+  }
+};
+
+int vgg_forward_impl(ibl_engine* e, const float* x, int N, int H, int W, float* feat_nhwc,
+                     cudaStream_t s) {
+  // largest activation: conv1_x output, N*H*W*64 values of 4 bytes (fp32, or bf16 hi + bf16 lo)
+  const size_t act_bytes = (size_t)N * H * W * 64 * 4;
+  IBL_RET(e->act[0].ensure(act_bytes));
+  IBL_RET(e->act[1].ensure(act_bytes));
+  int h = H, w = W;
+  int cur = 0;
+  if (e->conv_mode == IBL_CONV_SIMT_FP32) {
+    IBL_RET(launch_conv1_1(x, e->conv[0], N, h, w, false, e->act[0].as<float>(), nullptr, nullptr, s));
+    e->launches++;
+    for (int l = 1; l < 13; ++l) {
+      const ConvLayer& L = kVgg16[l];
+      const bool last = (l == 12);
+      float* dst = last ? feat_nhwc : e->act[cur ^ 1].as<float>();
+      IBL_RET(launch_conv3x3_simt(e->act[cur].as<float>(), e->conv[l], N, h, w, L.cin, L.cout, L.relu, dst, s));
+      e->launches++;
+      cur ^= 1;
+      if (L.pool) {
+        IBL_RET(launch_maxpool2x2(e->act[cur].as<float>(), N, h, w, L.cout, e->act[cur ^ 1].as<float>(), s));
+        e->launches++;
+        cur ^= 1;
+        h /= 2;
+        w /= 2;
+      }
+    }
+    return IBL_OK;
+  }
+  // tcgen05 path: activations are two bf16 planes, hi then lo, each `plane` elements apart
+  auto hi_of = [&](int b, size_t elems) { (void)elems; return e->act[b].as<__nv_bfloat16>(); };
+  auto lo_of = [&](int b, size_t elems) { return e->act[b].as<__nv_bfloat16>() + elems; };
+  size_t elems = (size_t)N * h * w * 64;
+  IBL_RET(launch_conv1_1(x, e->conv[0], N, h, w, true, nullptr, hi_of(0, elems), lo_of(0, elems), s));
+  e->launches++;
+  for (int l = 1; l < 13; ++l) {
+    const ConvLayer& L = kVgg16[l];
+    const bool last = (l == 12);
+    const size_t in_elems = (size_t)N * h * w * L.cin;
+    const int oh = L.pool ? h / 2 : h, ow = L.pool ? w / 2 : w;
+    const size_t out_elems = (size_t)N * oh * ow * L.cout;
+    IBL_RET(launch_conv3x3_tc(hi_of(cur, in_elems), lo_of(cur, in_elems), e->conv[l], N, h, w, L.cin,
+                              L.cout, L.relu, L.pool, last ? nullptr : hi_of(cur ^ 1, out_elems),
+                              last ? nullptr : lo_of(cur ^ 1, out_elems), last ? feat_nhwc : nullptr, s));
+    e->launches++;
+    cur ^= 1;
+    h = oh;
+    w = ow;
+  }
+  return IBL_OK;
+}
+
+}  // namespace
+
+extern "C" {
+
+int ibl_abi_version(void) { return IBLB200_ABI_VERSION; }
+
+const char* ibl_status_string(int status) {
+  switch (status) {
+    case IBL_OK: return "ok";
+    case IBL_ERR_BAD_ARG: return "bad argument";
+    case IBL_ERR_NOT_READY: return "parameters for this stage were not set";
+    case IBL_ERR_CUDA: return "CUDA error";
+    case IBL_ERR_NO_DEVICE: return "no usable sm_100 CUDA device (this library has no CPU fallback)";
+    case IBL_ERR_OOM: return "out of device memory";
+    case IBL_ERR_UNSUPPORTED: return "unsupported request";
+    default: return "unknown status";
+  }
+}
+
+const char* ibl_last_error(void) { return g_last_error.c_str(); }
+
+int ibl_engine_create(int device, ibl_engine** out) {
+  if (!out) return IBL_ERR_BAD_ARG;
+  *out = nullptr;
+  int count = 0;
+  if (cudaGetDeviceCount(&count) != cudaSuccess || count <= 0) {
+    cudaGetLastError();
+    set_last_error("no CUDA device visible; libiblb200 has no CPU fallback");
+    return IBL_ERR_NO_DEVICE;
+  }
+  IBL_REQUIRE(device >= 0 && device < count, "device index out of range");
+  cudaDeviceProp prop;
+  IBL_CUDA_OK(cudaGetDeviceProperties(&prop, device));
+  if (prop.major != 10) {
+    set_last_error(std::string("device '") + prop.name + "' is sm_" + std::to_string(prop.major) +
+                   std::to_string(prop.minor) + "; this library is built for sm_100a only");
+    return IBL_ERR_NO_DEVICE;
+  }
+  ibl_engine* e = new (std::nothrow) ibl_engine();
+  if (!e) return IBL_ERR_OOM;
+  e->device = device;
+  *out = e;
+  return IBL_OK;
+}
+
+int ibl_engine_destroy(ibl_engine* e) {
+  if (!e) return IBL_OK;
+  DeviceGuard g(e->device);
+  for (auto& c : e->conv) {
+    if (c.w_tck) cudaFree(c.w_tck);
+    if (c.bias) cudaFree(c.bias);
+    if (c.w_hi) cudaFree(c.w_hi);
+    if (c.w_lo) cudaFree(c.w_lo);
+  }
+  DevBuf* bufs[] = {&e->act[0], &e->act[1], &e->feat, &e->nv_assign, &e->nv_inv, &e->nv_raw, &e->vlad,
+                    &e->pca_partial, &e->qn, &e->dbn, &e->dist_chunk, &e->cand_d, &e->cand_i,
+                    &e->stage_in, &e->stage_out, &e->stage_out2};
+  for (DevBuf* b : bufs) b->release();
+  delete e;
+  return IBL_OK;
+}
+
+int ibl_engine_set_conv_mode(ibl_engine* e, int mode) {
+  IBL_REQUIRE(e, "null engine");
+  IBL_REQUIRE(mode == IBL_CONV_SIMT_FP32 || mode == IBL_CONV_TC_BF16X3, "unknown conv mode");
+  e->conv_mode = mode;
+  return IBL_OK;
+}
+int ibl_engine_get_conv_mode(ibl_engine* e, int* mode) {
+  IBL_REQUIRE(e && mode, "null argument");
+  *mode = e->conv_mode;
+  return IBL_OK;
+}
+int ibl_engine_launch_count(ibl_engine* e, uint64_t* count) {
+  IBL_REQUIRE(e && count, "null argument");
+  *count = e->launches;
+  return IBL_OK;
+}
+
+int ibl_engine_set_vgg16(ibl_engine* e, const float* const* w13, const float* const* b13, void* stream) {
+  IBL_REQUIRE(e && w13 && b13, "null argument");
+  DeviceGuard g(e->device);
+  for (int l = 0; l < 13; ++l) {
+    IBL_REQUIRE(w13[l] && b13[l], "null weight/bias pointer");
+    const ConvLayer& L = kVgg16[l];
+    ConvParams& p = e->conv[l];
+    const size_t nw = (size_t)L.cout * L.cin * 9;
+    if (!p.w_tck) IBL_CUDA_OK(cudaMalloc(&p.w_tck, nw * sizeof(float)));
+    if (!p.bias) IBL_CUDA_OK(cudaMalloc(&p.bias, L.cout * sizeof(float)));
+    if (L.cin % 64 == 0) {
+      if (!p.w_hi) IBL_CUDA_OK(cudaMalloc(&p.w_hi, nw * sizeof(__nv_bfloat16)));
+      if (!p.w_lo) IBL_CUDA_OK(cudaMalloc(&p.w_lo, nw * sizeof(__nv_bfloat16)));
+      p.cin_pad = L.cin;
+    }
+    IBL_RET(launch_repack_weights(w13[l], L.cout, L.cin, p, S(stream)));
+    IBL_CUDA_OK(cudaMemcpyAsync(p.bias, b13[l], L.cout * sizeof(float), cudaMemcpyDeviceToDevice, S(stream)));
+    e->launches++;
+  }
+  e->vgg_ready = true;
+  return IBL_OK;
+}
+
+int ibl_engine_set_netvlad(ibl_engine* e, const float* conv_w, const float* centroids, int K, int C,
+                           void* stream) {
+  (void)stream;
+  IBL_REQUIRE(e && conv_w && centroids, "null argument");
+  IBL_REQUIRE(K == 64, "NetVLAD kernels are built for K=64 clusters");
+  IBL_REQUIRE(C >= 4 && C % 4 == 0, "NetVLAD dim must be a positive multiple of 4");
+  e->nv_w = conv_w;
+  e->nv_c = centroids;
+  e->nv_K = K;
+  e->nv_C = C;
+  return IBL_OK;
+}
+
+int ibl_engine_set_pca(ibl_engine* e, const float* W, const float* b, int P, int D, void* stream) {
+  (void)stream;
+  IBL_REQUIRE(e && W && b, "null argument");
+  IBL_REQUIRE(P >= 1 && D >= 4 && D % 4 == 0, "bad PCA shape");
+  e->pca_W = W;
+  e->pca_b = b;
+  e->pca_P = P;
+  e->pca_D = D;
+  return IBL_OK;
+}
+
+int ibl_vgg16_forward(ibl_engine* e, const float* x, int N, int H, int W, float* feat_nhwc,
+                      float* feat_nchw, float* pool, void* stream) {
+  IBL_REQUIRE(e && x, "null argument");
+  IBL_REQUIRE(N >= 1 && H >= 16 && W >= 16, "VGG16 trunk needs N>=1 and H,W>=16");
+  if (!e->vgg_ready) { set_last_error("ibl_engine_set_vgg16 was not called"); return IBL_ERR_NOT_READY; }
+  DeviceGuard g(e->device);
+  const int fh = H / 16, fw = W / 16;
+  const size_t fbytes = (size_t)N * fh * fw * 512 * sizeof(float);
+  float* f = feat_nhwc;
+  if (!f) {
+    IBL_RET(e->feat.ensure(fbytes));
+    f = e->feat.as<float>();
+  }
+  IBL_RET(vgg_forward_impl(e, x, N, H, W, f, S(stream)));
+  if (feat_nchw) { IBL_RET(launch_nhwc_to_nchw(f, N, fh * fw, 512, feat_nchw, S(stream))); e->launches++; }
+  if (pool) { IBL_RET(launch_global_maxpool_nhwc(f, N, fh * fw, 512, pool, S(stream))); e->launches++; }
+  return IBL_OK;
+}
+
+int ibl_netvlad_forward(ibl_engine* e, const float* feat, int nhwc, int N, int C, int S_, const float* conv_w,
+                        const float* centroids, int K, int normalize_input, float* vlad_raw,
+                        float* vlad_norm, void* stream) {
+  IBL_REQUIRE(e && feat && conv_w && centroids, "null argument");
+  IBL_REQUIRE(N >= 1 && C >= 1 && S_ >= 1, "empty NetVLAD input");
+  IBL_REQUIRE(K == 64, "NetVLAD kernels are built for K=64 clusters");
+  IBL_REQUIRE(vlad_raw || vlad_norm, "no output requested");
+  DeviceGuard g(e->device);
+  IBL_RET(e->nv_assign.ensure((size_t)N * S_ * K * sizeof(float)));
+  IBL_RET(e->nv_inv.ensure((size_t)N * S_ * sizeof(float)));
+  float* raw = vlad_raw;
+  if (!raw) {
+    IBL_RET(e->nv_raw.ensure((size_t)N * K * C * sizeof(float)));
+    raw = e->nv_raw.as<float>();
+  }
+  return launch_netvlad(feat, nhwc != 0, N, C, S_, conv_w, centroids, K, normalize_input != 0,
+                        e->nv_assign.as<float>(), e->nv_inv.as<float>(), nullptr, raw, vlad_norm,
+                        S(stream), &e->launches);
+}
+
+int ibl_vlad_normalize(ibl_engine* e, const float* vlad_raw, int N, int K, int C, float* out, void* stream) {
+  IBL_REQUIRE(e && vlad_raw && out, "null argument");
+  IBL_REQUIRE(N >= 1 && K >= 1 && C >= 1 && K <= 4096, "bad shape");
+  DeviceGuard g(e->device);
+  e->launches++;
+  return launch_vlad_normalize(vlad_raw, N, K, C, out, S(stream));
+}
+
+int ibl_pca_l2(ibl_engine* e, const float* v, int N, int D, const float* W, const float* b, int P,
+               float* out, void* stream) {
+  IBL_REQUIRE(e && v && W && b && out, "null argument");
+  IBL_REQUIRE(N >= 1 && P >= 1 && D >= 4, "bad shape");
+  IBL_REQUIRE((size_t)P * sizeof(float) <= 48 * 1024, "PCA output dim above 12288 is not supported");
+  DeviceGuard g(e->device);
+  // enough K-splits to fill the machine: tiles = ceil(P/128)*ceil(N/64)*splits >= ~2 waves of 148 SMs
+  int tiles = cdiv(P, 128) * cdiv(N, 64);
+  int splits = cdiv(2 * 148, tiles);
+  if (splits < 1) splits = 1;
+  if (splits > 32) splits = 32;
+  while (splits > 1 && D / splits < 256) --splits;
+  IBL_RET(e->pca_partial.ensure((size_t)splits * N * P * sizeof(float)));
+  return launch_pca_l2(v, N, D, W, b, P, e->pca_partial.as<float>(), splits, out, S(stream), &e->launches);
+}
+
+int ibl_l2_normalize_rows(ibl_engine* e, const float* x, int N, int D, float* out, void* stream) {
+  IBL_REQUIRE(e && x && out, "null argument");
+  IBL_REQUIRE(N >= 0 && D >= 1, "bad shape");
+  DeviceGuard g(e->device);
+  e->launches++;
+  return launch_l2_normalize_rows(x, N, D, out, S(stream));
+}
+
+int ibl_extract(ibl_engine* e, const float* x, int N, int H, int W, unsigned flags, float* out,
+                float* pool, void* stream) {
+  IBL_REQUIRE(e && x && out, "null argument");
+  IBL_REQUIRE(flags & IBL_OUT_VLAD, "ibl_extract: IBL_OUT_VLAD is required");
+  IBL_REQUIRE(!(flags & IBL_OUT_POOL) || pool, "IBL_OUT_POOL needs a pool buffer");
+  IBL_REQUIRE(N >= 1 && H >= 16 && W >= 16, "VGG16 trunk needs N>=1 and H,W>=16");
+  if (!e->vgg_ready || !e->nv_w) { set_last_error("VGG16 / NetVLAD parameters were not set"); return IBL_ERR_NOT_READY; }
+  const bool pca = (flags & IBL_OUT_PCA) != 0;
+  if (pca && !e->pca_W) { set_last_error("PCA parameters were not set"); return IBL_ERR_NOT_READY; }
+  IBL_REQUIRE(e->nv_C == 512, "NetVLAD dim must match the VGG16 feature dim (512)");
+  DeviceGuard g(e->device);
+  const int fh = H / 16, fw = W / 16, Sp = fh * fw;
+  const int K = e->nv_K, C = e->nv_C, D = K * C;
+  if (pca) IBL_REQUIRE(e->pca_D == D, "PCA input dim must equal K*C");
+  const int out_dim = pca ? e->pca_P : D;
+  // micro-batches bound the workspace (157 MB / image at 480x640)
+  const int MB = 32;
+  for (int n0 = 0; n0 < N; n0 += MB) {
+    const int nb = (N - n0 < MB) ? (N - n0) : MB;
+    const float* xb = x + (size_t)n0 * 3 * H * W;
+    IBL_RET(e->feat.ensure((size_t)nb * Sp * 512 * sizeof(float)));
+    IBL_RET(vgg_forward_impl(e, xb, nb, H, W, e->feat.as<float>(), S(stream)));
+    if (flags & IBL_OUT_POOL) {
+      IBL_RET(launch_global_maxpool_nhwc(e->feat.as<float>(), nb, Sp, 512, pool + (size_t)n0 * 512, S(stream)));
+      e->launches++;
+    }
+    float* vdst = out + (size_t)n0 * out_dim;
+    if (pca) {
+      IBL_RET(e->vlad.ensure((size_t)nb * D * sizeof(float)));
+      vdst = e->vlad.as<float>();
+    }
+    IBL_RET(ibl_netvlad_forward(e, e->feat.as<float>(), 1, nb, C, Sp, e->nv_w, e->nv_c, K, 1, nullptr, vdst, stream));
+    if (pca)
+      IBL_RET(ibl_pca_l2(e, vdst, nb, D, e->pca_W, e->pca_b, e->pca_P, out + (size_t)n0 * out_dim, stream));
+  }
+  return IBL_OK;
+}
+
+int ibl_extract_host(ibl_engine* e, const float* x_host, int N, int H, int W, unsigned flags,
+                     float* out_host, float* pool_host, void* stream) {
+  IBL_REQUIRE(e && x_host && out_host, "null argument");
+  IBL_REQUIRE(N >= 1 && H >= 16 && W >= 16, "VGG16 trunk needs N>=1 and H,W>=16");
+  DeviceGuard g(e->device);
+  const bool pca = (flags & IBL_OUT_PCA) != 0;
+  const int out_dim = pca ? e->pca_P : e->nv_K * e->nv_C;
+  const size_t in_bytes = (size_t)N * 3 * H * W * sizeof(float);
+  IBL_RET(e->stage_in.ensure(in_bytes));
+  IBL_RET(e->stage_out.ensure((size_t)N * out_dim * sizeof(float)));
+  if (flags & IBL_OUT_POOL) IBL_RET(e->stage_out2.ensure((size_t)N * 512 * sizeof(float)));
+  IBL_CUDA_OK(cudaMemcpyAsync(e->stage_in.p, x_host, in_bytes, cudaMemcpyHostToDevice, S(stream)));
+  IBL_RET(ibl_extract(e, e->stage_in.as<float>(), N, H, W, flags, e->stage_out.as<float>(),
+                      (flags & IBL_OUT_POOL) ? e->stage_out2.as<float>() : nullptr, stream));
+  IBL_CUDA_OK(cudaMemcpyAsync(out_host, e->stage_out.p, (size_t)N * out_dim * sizeof(float),
+                              cudaMemcpyDeviceToHost, S(stream)));
+  if ((flags & IBL_OUT_POOL) && pool_host)
+    IBL_CUDA_OK(cudaMemcpyAsync(pool_host, e->stage_out2.p, (size_t)N * 512 * sizeof(float),
+                                cudaMemcpyDeviceToHost, S(stream)));
+  IBL_CUDA_OK(cudaStreamSynchronize(S(stream)));
+  return IBL_OK;
+}
+
+int ibl_l2dist_dense(ibl_engine* e, const float* q, int m, const float* db, int n, int d, float* out,
+                     void* stream) {
+  IBL_REQUIRE(e && q && db && out, "null argument");
+  IBL_REQUIRE(m >= 1 && n >= 1 && d >= 4 && d % 4 == 0, "bad shape");
+  DeviceGuard g(e->device);
+  IBL_RET(e->qn.ensure((size_t)m * sizeof(float)));
+  IBL_RET(e->dbn.ensure((size_t)n * sizeof(float)));
+  IBL_RET(launch_row_sqnorm(q, m, d, e->qn.as<float>(), S(stream)));
+  IBL_RET(launch_row_sqnorm(db, n, d, e->dbn.as<float>(), S(stream)));
+  IBL_RET(launch_l2dist_dense(q, e->qn.as<float>(), m, db, e->dbn.as<float>(), n, d, out, n, S(stream)));
+  e->launches += 3;
+  return IBL_OK;
+}
+
+int ibl_l2dist_topk(ibl_engine* e, const float* q, int m, const float* db, int n, int n_valid, int d,
+                    int k, int64_t idx_base, float* out_dist, int64_t* out_idx, void* stream) {
+  IBL_REQUIRE(e && q && db && out_dist && out_idx, "null argument");
+  IBL_REQUIRE(m >= 1 && n >= 1 && d >= 4 && d % 4 == 0, "bad shape");
+  IBL_REQUIRE(n_valid >= 0 && n_valid <= n, "n_valid out of range");
+  IBL_REQUIRE(k >= 1 && k <= 128, "top-k supports 1 <= k <= 128");
+  DeviceGuard g(e->device);
+  const int CH = 32768;                         // database rows per dense chunk
+  const int nch = n_valid > 0 ? cdiv(n_valid, CH) : 1;
+  IBL_REQUIRE((long long)nch * k <= 8192, "database shard too large for one call; shard it");
+  IBL_RET(e->qn.ensure((size_t)m * sizeof(float)));
+  IBL_RET(e->dbn.ensure((size_t)n * sizeof(float)));
+  const int chw = n_valid < CH ? (n_valid > 0 ? n_valid : 1) : CH;
+  IBL_RET(e->dist_chunk.ensure((size_t)m * chw * sizeof(float)));
+  IBL_RET(launch_row_sqnorm(q, m, d, e->qn.as<float>(), S(stream)));
+  IBL_RET(launch_row_sqnorm(db, n, d, e->dbn.as<float>(), S(stream)));
+  e->launches += 2;
+  float* cd = out_dist;
+  int64_t* ci = out_idx;
+  if (nch > 1) {
+    IBL_RET(e->cand_d.ensure((size_t)nch * m * k * sizeof(float)));
+    IBL_RET(e->cand_i.ensure((size_t)nch * m * k * sizeof(int64_t)));
+    cd = e->cand_d.as<float>();
+    ci = e->cand_i.as<int64_t>();
+  }
+  for (int c = 0; c < nch; ++c) {
+    const int j0 = c * CH;
+    const int nc = (n_valid - j0 < CH) ? (n_valid - j0) : CH;
+    if (nc > 0)
+      IBL_RET(launch_l2dist_dense(q, e->qn.as<float>(), m, db + (size_t)j0 * d, e->dbn.as<float>() + j0, nc,
+                                  d, e->dist_chunk.as<float>(), chw, S(stream)));
+    IBL_RET(launch_topk_rows(e->dist_chunk.as<float>(), chw, m, nc > 0 ? nc : 0, k, idx_base + j0,
+                             cd + (size_t)c * m * k, ci + (size_t)c * m * k, false, S(stream)));
+    e->launches += 2;
+  }
+  if (nch > 1) {
+    IBL_RET(launch_topk_merge(cd, ci, nch, m, k, k, out_dist, out_idx, S(stream)));
+    e->launches++;
+  }
+  return IBL_OK;
+}
+
+int ibl_topk_rows(ibl_engine* e, const float* dist, int m, int n, int k, float* out_dist, int64_t* out_idx,
+                  void* stream) {
+  IBL_REQUIRE(e && dist && out_dist && out_idx, "null argument");
+  IBL_REQUIRE(m >= 0 && n >= 1 && k >= 1 && k <= 128, "bad shape");
+  DeviceGuard g(e->device);
+  e->launches++;
+  return launch_topk_rows(dist, n, m, n, k, 0, out_dist, out_idx, false, S(stream));
+}
+
+int ibl_topk_merge(ibl_engine* e, const float* cand_dist, const int64_t* cand_idx, int parts, int m,
+                   int k_in, int k_out, float* out_dist, int64_t* out_idx, void* stream) {
+  IBL_REQUIRE(e && cand_dist && cand_idx && out_dist && out_idx, "null argument");
+  IBL_REQUIRE(parts >= 1 && m >= 0 && k_in >= 1, "bad shape");
+  DeviceGuard g(e->device);
+  e->launches++;
+  return launch_topk_merge(cand_dist, cand_idx, parts, m, k_in, k_out, out_dist, out_idx, S(stream));
+}
+
+int ibl_l2dist_topk_host(ibl_engine* e, const float* q_host, int m, const float* db_host, int n, int d,
+                         int k, float* out_dist_host, int64_t* out_idx_host, void* stream) {
+  IBL_REQUIRE(e && q_host && db_host && out_dist_host && out_idx_host, "null argument");
+  IBL_REQUIRE(m >= 1 && n >= 1 && d >= 4 && k >= 1 && k <= 128, "bad shape");
+  DeviceGuard g(e->device);
+  const size_t qb = (size_t)m * d * sizeof(float), dbb = (size_t)n * d * sizeof(float);
+  IBL_RET(e->stage_in.ensure(qb + dbb));
+  IBL_RET(e->stage_out.ensure((size_t)m * k * sizeof(float)));
+  IBL_RET(e->stage_out2.ensure((size_t)m * k * sizeof(int64_t)));
+  float* dq = e->stage_in.as<float>();
+  float* ddb = dq + (size_t)m * d;
+  IBL_CUDA_OK(cudaMemcpyAsync(dq, q_host, qb, cudaMemcpyHostToDevice, S(stream)));
+  IBL_CUDA_OK(cudaMemcpyAsync(ddb, db_host, dbb, cudaMemcpyHostToDevice, S(stream)));
+  IBL_RET(ibl_l2dist_topk(e, dq, m, ddb, n, n, d, k, 0, e->stage_out.as<float>(), e->stage_out2.as<int64_t>(), stream));
+  IBL_CUDA_OK(cudaMemcpyAsync(out_dist_host, e->stage_out.p, (size_t)m * k * sizeof(float), cudaMemcpyDeviceToHost, S(stream)));
+  IBL_CUDA_OK(cudaMemcpyAsync(out_idx_host, e->stage_out2.p, (size_t)m * k * sizeof(int64_t), cudaMemcpyDeviceToHost, S(stream)));
+  IBL_CUDA_OK(cudaStreamSynchronize(S(stream)));
+  return IBL_OK;
+}
+
+int ibl_selftest_tc(ibl_engine* e, float* max_rel_err) {
+  IBL_REQUIRE(e, "null engine");
+  DeviceGuard g(e->device);
+  return tc_selftest(max_rel_err, nullptr);
+}
+
+// One conv layer in isolation, fp32 NHWC in / out, either math mode (test hook).
+int ibl_debug_conv3x3(ibl_engine* e, const float* x_nhwc, int N, int H, int W, int cin, const float* w_oihw,
+                      const float* bias, int cout, int relu, int pool, int mode, int bn_override,
+                      float* y_nhwc, void* stream) {
+  IBL_REQUIRE(e && x_nhwc && w_oihw && bias && y_nhwc, "null argument");
+  IBL_REQUIRE(cin % 64 == 0 && cout % 64 == 0, "debug conv needs Cin%64==0, Cout%64==0");
+  DeviceGuard g(e->device);
+  cudaStream_t s = S(stream);
+  ConvParams p;
+  const size_t nw = (size_t)cout * cin * 9;
+  IBL_CUDA_OK(cudaMalloc(&p.w_tck, nw * 4));
+  IBL_CUDA_OK(cudaMalloc(&p.bias, cout * 4));
+  IBL_CUDA_OK(cudaMalloc(&p.w_hi, nw * 2));
+  IBL_CUDA_OK(cudaMalloc(&p.w_lo, nw * 2));
+  int rc = launch_repack_weights(w_oihw, cout, cin, p, s);
+  cudaMemcpyAsync(p.bias, bias, cout * 4, cudaMemcpyDeviceToDevice, s);
+  const size_t in_e = (size_t)N * H * W * cin;
+  const int oh = pool ? H / 2 : H, ow = pool ? W / 2 : W;
+  const size_t out_e = (size_t)N * oh * ow * cout;
+  if (rc == IBL_OK && mode == IBL_CONV_SIMT_FP32) {
+    if (!pool) {
+      rc = launch_conv3x3_simt(x_nhwc, p, N, H, W, cin, cout, relu != 0, y_nhwc, s);
+    } else {
+      float* tmp = nullptr;
+      if (cudaMalloc(&tmp, (size_t)N * H * W * cout * 4) != cudaSuccess) rc = IBL_ERR_OOM;
+      if (rc == IBL_OK) rc = launch_conv3x3_simt(x_nhwc, p, N, H, W, cin, cout, relu != 0, tmp, s);
+      if (rc == IBL_OK) rc = launch_maxpool2x2(tmp, N, H, W, cout, y_nhwc, s);
+      cudaStreamSynchronize(s);
+      if (tmp) cudaFree(tmp);
+    }
+  } else if (rc == IBL_OK) {
+    __nv_bfloat16 *xh = nullptr, *xl = nullptr;
+    if (cudaMalloc(&xh, in_e * 2) != cudaSuccess || cudaMalloc(&xl, in_e * 2) != cudaSuccess) rc = IBL_ERR_OOM;
+    if (rc == IBL_OK) rc = launch_f32_to_planes(x_nhwc, in_e, xh, xl, s);
+    tc_set_bn_override(bn_override);
+    if (mode == 2) {
+      __nv_bfloat16 *yh = nullptr, *yl = nullptr;
+      if (cudaMalloc(&yh, out_e * 2) != cudaSuccess || cudaMalloc(&yl, out_e * 2) != cudaSuccess) rc = IBL_ERR_OOM;
+      if (rc == IBL_OK) rc = launch_conv3x3_tc(xh, xl, p, N, H, W, cin, cout, relu != 0, pool != 0, yh, yl, nullptr, s);
+      if (rc == IBL_OK) rc = launch_planes_to_f32(yh, yl, out_e, y_nhwc, s);
+      cudaStreamSynchronize(s);
+      if (yh) cudaFree(yh);
+      if (yl) cudaFree(yl);
+    } else if (rc == IBL_OK) {
+      rc = launch_conv3x3_tc(xh, xl, p, N, H, W, cin, cout, relu != 0, pool != 0, nullptr, nullptr, y_nhwc, s);
+    }
+    tc_set_bn_override(0);
+    cudaStreamSynchronize(s);
+    if (xh) cudaFree(xh);
+    if (xl) cudaFree(xl);
+  }
+  cudaError_t ce = cudaStreamSynchronize(s);
+  cudaFree(p.w_tck); cudaFree(p.bias); cudaFree(p.w_hi); cudaFree(p.w_lo);
+  if (rc == IBL_OK && ce != cudaSuccess) {
+    set_last_error(std::string("debug conv: ") + cudaGetErrorString(ce));
+    return IBL_ERR_CUDA;
+  }
+  e->launches += 3;
+  return rc;
+}
+
+}  // extern "C"

@@ -1,0 +1,428 @@
+// 3x3 / stride 1 / pad 1 convolution as a tcgen05 implicit GEMM (reference: the 12 convs
+// conv1_2..conv5_3 of ibl/models/vgg.py:40-42,61-62, cuDNN in the reference).
+//
+//   M = output pixels (128 per tile: TH x TW patch of one image)
+//   N = output channels (BN per tile)
+//   K = 9 taps x Cin, walked as (tap, 64-channel chunk)
+//
+// fp32 parity on a tensor core without an fp32 mode: every fp32 operand is carried as two bf16
+// planes (hi = bf16(x), lo = bf16(x - hi)) and each K-chunk issues three MMAs
+//   A_hi.B_hi + A_hi.B_lo + A_lo.B_hi      (fp32 accumulation in TMEM),
+// dropping only the lo.lo term (~2^-16 relative).  Activations live in HBM as NHWC bf16 hi/lo
+// planes, weights as [tap][Cout][Cin] hi/lo planes, so every operand tile is one TMA box:
+// the activation box for tap (kh,kw) is the output patch shifted by (kh-1,kw-1) and the
+// hardware zero-fills the out-of-image part, which is exactly the conv's zero padding.
+//
+// Warp roles (192 threads, persistent over tiles):
+//   warp 0  TMA producer      warp 1  MMA issuer + TMEM owner      warps 2-5  epilogue
+// Two TMEM accumulator buffers let the epilogue of tile i overlap the main loop of tile i+1.
+// Epilogue: TMEM -> registers, + bias, ReLU, optional fused 2x2 max-pool (warp shuffles),
+// split into hi/lo planes (or fp32 for conv5_3), 16-byte stores.
+#include "common.cuh"
+#include "tc_common.cuh"
+
+namespace ibl {
+
+using namespace tc;
+
+// ---- host: driver entry point ---------------------------------------------------------------
+namespace tc {
+EncodeTiledFn get_encode_tiled() {
+  static EncodeTiledFn fn = nullptr;
+  static bool tried = false;
+  if (!tried) {
+    tried = true;
+    void* p = nullptr;
+    cudaDriverEntryPointQueryResult qres;
+    if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &qres) ==
+            cudaSuccess &&
+        qres == cudaDriverEntryPointSuccess)
+      fn = reinterpret_cast<EncodeTiledFn>(p);
+  }
+  return fn;
+}
+
+int make_tmap(CUtensorMap* out, CUtensorMapDataType dt, int rank, const void* base,
+              const uint64_t* dims, const uint64_t* strides_bytes, const uint32_t* box) {
+  EncodeTiledFn enc = get_encode_tiled();
+  if (!enc) {
+    set_last_error("cuTensorMapEncodeTiled is not available (no CUDA driver?)");
+    return IBL_ERR_NO_DEVICE;
+  }
+  cuuint64_t gdim[5];
+  cuuint64_t gstr[5];
+  cuuint32_t bx[5], es[5];
+  for (int i = 0; i < rank; ++i) {
+    gdim[i] = dims[i];
+    bx[i] = box[i];
+    es[i] = 1;
+  }
+  for (int i = 0; i + 1 < rank; ++i) gstr[i] = strides_bytes[i];
+  CUresult r = enc(out, dt, (cuuint32_t)rank, const_cast<void*>(base), gdim, gstr, bx, es,
+                   CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B,
+                   CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  if (r != CUDA_SUCCESS) {
+    set_last_error("cuTensorMapEncodeTiled failed with CUresult " + std::to_string((int)r));
+    return IBL_ERR_CUDA;
+  }
+  return IBL_OK;
+}
+}  // namespace tc
+
+int tc_driver_init() { return get_encode_tiled() ? IBL_OK : IBL_ERR_NO_DEVICE; }
+
+// ---- kernel ---------------------------------------------------------------------------------
+struct ConvTcArgs {
+  int N, H, W, cin, cout;
+  int tw_log2;            // TW = 1 << tw_log2 (8 or 16), TH = 128 / TW
+  int tiles_w, tiles_h;   // patches per image
+  int n_tiles;            // cout / BN
+  int total_tiles;        // N * tiles_h * tiles_w * n_tiles
+  int relu, pool;
+  const float* bias;
+  __nv_bfloat16* y_hi;
+  __nv_bfloat16* y_lo;
+  float* y_f32;
+};
+
+constexpr int TC_BM = 128;
+constexpr int TC_BK = 64;                       // bf16 elements per K-chunk = one 128-byte row
+constexpr int TC_A_BYTES = TC_BM * TC_BK * 2;   // 16 KiB per plane
+
+template <int BN>
+struct ConvTcSmem {
+  static constexpr int B_BYTES = BN * TC_BK * 2;
+  static constexpr int STAGE_BYTES = 2 * TC_A_BYTES + 2 * B_BYTES;
+};
+
+__device__ __forceinline__ uint32_t pack_bf16x2(float a, float b) {
+  __nv_bfloat162 t = __floats2bfloat162_rn(a, b);
+  return *reinterpret_cast<uint32_t*>(&t);
+}
+
+template <int BN, int STAGES>
+__global__ void __launch_bounds__(192, 1)
+conv3x3_tc_kernel(const __grid_constant__ CUtensorMap tm_xhi, const __grid_constant__ CUtensorMap tm_xlo,
+                  const __grid_constant__ CUtensorMap tm_whi, const __grid_constant__ CUtensorMap tm_wlo,
+                  const ConvTcArgs a) {
+  extern __shared__ __align__(1024) uint8_t smem_raw[];
+  // 1024-byte alignment is required by the 128B swizzle; dynamic smem base is only 16B-aligned
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  constexpr int B_BYTES = ConvTcSmem<BN>::B_BYTES;
+  constexpr int STAGE_BYTES = ConvTcSmem<BN>::STAGE_BYTES;
+  uint64_t* bars = reinterpret_cast<uint64_t*>(smem + STAGES * STAGE_BYTES);
+  uint64_t* full_bar = bars;
+  uint64_t* empty_bar = bars + STAGES;
+  uint64_t* tfull_bar = bars + 2 * STAGES;
+  uint64_t* tempty_bar = bars + 2 * STAGES + 2;
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 2 * STAGES + 4);
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  constexpr uint32_t TMEM_COLS = 2 * BN;  // 128, 256 or 512: a power of two >= 32
+
+  if (warp == 0 && lane == 0) {
+    tma_prefetch_desc(&tm_xhi);
+    tma_prefetch_desc(&tm_xlo);
+    tma_prefetch_desc(&tm_whi);
+    tma_prefetch_desc(&tm_wlo);
+    for (int i = 0; i < STAGES; ++i) {
+      mbar_init(&full_bar[i], 1);
+      mbar_init(&empty_bar[i], 1);
+    }
+    mbar_init(&tfull_bar[0], 1);
+    mbar_init(&tfull_bar[1], 1);
+    mbar_init(&tempty_bar[0], 4);
+    mbar_init(&tempty_bar[1], 4);
+    fence_barrier_init();
+    fence_proxy_async();
+  }
+  if (warp == 1) {
+    tmem_alloc(tmem_slot, TMEM_COLS);
+    tmem_relinquish();
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+
+  const int TW = 1 << a.tw_log2;
+  const int kchunks = a.cin / TC_BK;
+  const int kiters = 9 * kchunks;
+  const int tiles_per_img = a.tiles_h * a.tiles_w;
+
+  if (warp == 0) {
+    // ================= TMA producer =================
+    if (lane == 0) {
+      int stage = 0;
+      uint32_t phase = 0;
+      for (int tile = blockIdx.x; tile < a.total_tiles; tile += gridDim.x) {
+        const int nt = tile % a.n_tiles;
+        const int pt = tile / a.n_tiles;
+        const int img = pt / tiles_per_img;
+        const int rem = pt - img * tiles_per_img;
+        const int h0 = (rem / a.tiles_w) * (TC_BM >> a.tw_log2);
+        const int w0 = (rem % a.tiles_w) * TW;
+        const int n0 = nt * BN;
+        for (int kit = 0; kit < kiters; ++kit) {
+          const int tap = kit / kchunks;
+          const int c0 = (kit - tap * kchunks) * TC_BK;
+          const int kh = tap / 3 - 1, kw = tap % 3 - 1;
+          mbar_wait(&empty_bar[stage], phase ^ 1);
+          uint8_t* st = smem + stage * STAGE_BYTES;
+          mbar_arrive_expect_tx(&full_bar[stage], STAGE_BYTES);
+          tma_load_4d(st, &tm_xhi, &full_bar[stage], c0, w0 + kw, h0 + kh, img);
+          tma_load_4d(st + TC_A_BYTES, &tm_xlo, &full_bar[stage], c0, w0 + kw, h0 + kh, img);
+          tma_load_3d(st + 2 * TC_A_BYTES, &tm_whi, &full_bar[stage], c0, n0, tap);
+          tma_load_3d(st + 2 * TC_A_BYTES + B_BYTES, &tm_wlo, &full_bar[stage], c0, n0, tap);
+          if (++stage == STAGES) { stage = 0; phase ^= 1; }
+        }
+      }
+    }
+  } else if (warp == 1) {
+    // ================= MMA issuer =================
+    if (lane == 0) {
+      constexpr uint32_t idesc = umma_idesc_bf16_f32(TC_BM, BN);
+      int stage = 0;
+      uint32_t phase = 0;
+      int it = 0;
+      for (int tile = blockIdx.x; tile < a.total_tiles; tile += gridDim.x, ++it) {
+        const int as = it & 1;
+        const uint32_t aphase = (it >> 1) & 1;
+        mbar_wait(&tempty_bar[as], aphase ^ 1);
+        tc_fence_after();
+        const uint32_t d_tmem = tmem_base + as * BN;
+        for (int kit = 0; kit < kiters; ++kit) {
+          mbar_wait(&full_bar[stage], phase);
+          tc_fence_after();
+          const uint32_t sa = smem_u32(smem + stage * STAGE_BYTES);
+          const uint64_t a_hi = umma_desc_kmajor_sw128(sa);
+          const uint64_t a_lo = umma_desc_kmajor_sw128(sa + TC_A_BYTES);
+          const uint64_t b_hi = umma_desc_kmajor_sw128(sa + 2 * TC_A_BYTES);
+          const uint64_t b_lo = umma_desc_kmajor_sw128(sa + 2 * TC_A_BYTES + B_BYTES);
+#pragma unroll
+          for (int k = 0; k < TC_BK / 16; ++k) {
+            // advance 16 bf16 = 32 bytes inside the 128-byte swizzle row: +2 in 16-byte units
+            const uint64_t ko = (uint64_t)(k * 2);
+            umma_bf16(d_tmem, a_lo + ko, b_hi + ko, idesc, (kit > 0 || k > 0) ? 1u : 0u);
+            umma_bf16(d_tmem, a_hi + ko, b_lo + ko, idesc, 1u);
+            umma_bf16(d_tmem, a_hi + ko, b_hi + ko, idesc, 1u);
+          }
+          umma_commit(&empty_bar[stage]);   // frees the smem slot when these MMAs retire
+          if (++stage == STAGES) { stage = 0; phase ^= 1; }
+        }
+        umma_commit(&tfull_bar[as]);        // accumulator ready for the epilogue
+      }
+    }
+  } else {
+    // ================= epilogue (warps 2..5) =================
+    const int q = warp & 3;                 // TMEM lane quarter this warp may access
+    const int m = q * 32 + lane;            // accumulator row = pixel index inside the patch
+    const int r = m >> a.tw_log2, c = m & (TW - 1);
+    int it = 0;
+    for (int tile = blockIdx.x; tile < a.total_tiles; tile += gridDim.x, ++it) {
+      const int as = it & 1;
+      const uint32_t aphase = (it >> 1) & 1;
+      const int nt = tile % a.n_tiles;
+      const int pt = tile / a.n_tiles;
+      const int img = pt / tiles_per_img;
+      const int rem = pt - img * tiles_per_img;
+      const int h0 = (rem / a.tiles_w) * (TC_BM >> a.tw_log2);
+      const int w0 = (rem % a.tiles_w) * TW;
+      const int n0 = nt * BN;
+      const int h = h0 + r, w = w0 + c;
+      bool valid;
+      long long pix;
+      if (a.pool) {
+        const int OH = a.H >> 1, OW = a.W >> 1;
+        const int oh = h >> 1, ow = w >> 1;
+        valid = ((r & 1) == 0) && ((c & 1) == 0) && oh < OH && ow < OW;
+        pix = ((long long)img * OH + oh) * OW + ow;
+      } else {
+        valid = h < a.H && w < a.W;
+        pix = ((long long)img * a.H + h) * a.W + w;
+      }
+      mbar_wait(&tfull_bar[as], aphase);
+      tc_fence_after();
+      const uint32_t t_row = tmem_base + ((uint32_t)(q * 32) << 16) + as * BN;
+#pragma unroll 1
+      for (int ch = 0; ch < BN / 32; ++ch) {
+        uint32_t raw[32];
+        tmem_ld_32x32(t_row + ch * 32, raw);
+        tmem_ld_wait();
+        float v[32];
+        const float4* bp = reinterpret_cast<const float4*>(a.bias + n0 + ch * 32);
+#pragma unroll
+        for (int j = 0; j < 8; ++j) {
+          const float4 b = __ldg(bp + j);
+          v[4 * j + 0] = __uint_as_float(raw[4 * j + 0]) + b.x;
+          v[4 * j + 1] = __uint_as_float(raw[4 * j + 1]) + b.y;
+          v[4 * j + 2] = __uint_as_float(raw[4 * j + 2]) + b.z;
+          v[4 * j + 3] = __uint_as_float(raw[4 * j + 3]) + b.w;
+        }
+        if (a.relu) {
+#pragma unroll
+          for (int j = 0; j < 32; ++j) v[j] = fmaxf(v[j], 0.f);
+        }
+        if (a.pool) {
+#pragma unroll
+          for (int j = 0; j < 32; ++j) {
+            v[j] = fmaxf(v[j], __shfl_xor_sync(0xffffffffu, v[j], 1));
+            v[j] = fmaxf(v[j], __shfl_xor_sync(0xffffffffu, v[j], TW));
+          }
+        }
+        if (valid) {
+          const long long off = pix * a.cout + n0 + ch * 32;
+          if (a.y_f32) {
+            float4* o = reinterpret_cast<float4*>(a.y_f32 + off);
+#pragma unroll
+            for (int j = 0; j < 8; ++j) o[j] = make_float4(v[4 * j], v[4 * j + 1], v[4 * j + 2], v[4 * j + 3]);
+          } else {
+            uint32_t hi[16], lo[16];
+#pragma unroll
+            for (int j = 0; j < 16; ++j) {
+              const float x0 = v[2 * j], x1 = v[2 * j + 1];
+              const __nv_bfloat16 h0b = __float2bfloat16_rn(x0), h1b = __float2bfloat16_rn(x1);
+              __nv_bfloat162 hh(h0b, h1b);
+              hi[j] = *reinterpret_cast<uint32_t*>(&hh);
+              lo[j] = pack_bf16x2(x0 - __bfloat162float(h0b), x1 - __bfloat162float(h1b));
+            }
+            uint4* oh4 = reinterpret_cast<uint4*>(a.y_hi + off);
+            uint4* ol4 = reinterpret_cast<uint4*>(a.y_lo + off);
+#pragma unroll
+            for (int j = 0; j < 4; ++j) {
+              oh4[j] = make_uint4(hi[4 * j], hi[4 * j + 1], hi[4 * j + 2], hi[4 * j + 3]);
+              ol4[j] = make_uint4(lo[4 * j], lo[4 * j + 1], lo[4 * j + 2], lo[4 * j + 3]);
+            }
+          }
+        }
+      }
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(&tempty_bar[as]);
+    }
+  }
+
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 1) {
+    tc_fence_after();
+    tmem_dealloc(tmem_base, TMEM_COLS);
+  }
+}
+
+// ---- host launcher --------------------------------------------------------------------------
+template <int BN, int STAGES>
+static int launch_tc_variant(const CUtensorMap& xhi, const CUtensorMap& xlo, const CUtensorMap& whi,
+                             const CUtensorMap& wlo, const ConvTcArgs& a, cudaStream_t s) {
+  constexpr int smem = STAGES * ConvTcSmem<BN>::STAGE_BYTES + 1024 /*align slack*/ + 256 /*barriers*/;
+  static bool attr_done = false;
+  if (!attr_done) {
+    IBL_CUDA_OK(cudaFuncSetAttribute(conv3x3_tc_kernel<BN, STAGES>,
+                                     cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
+    attr_done = true;
+  }
+  int dev = 0, sms = 148;
+  cudaGetDevice(&dev);
+  cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+  int grid = a.total_tiles < sms ? a.total_tiles : sms;
+  conv3x3_tc_kernel<BN, STAGES><<<grid, 192, smem, s>>>(xhi, xlo, whi, wlo, a);
+  IBL_CUDA_OK(cudaGetLastError());
+  return IBL_OK;
+}
+
+static int g_tc_bn_override = 0;   // test hook: force BN (64/128/256) where it divides Cout
+void tc_set_bn_override(int bn) { g_tc_bn_override = bn; }
+
+int launch_conv3x3_tc(const __nv_bfloat16* x_hi, const __nv_bfloat16* x_lo, const ConvParams& p,
+                      int N, int H, int W, int cin, int cout, bool relu, bool pool,
+                      __nv_bfloat16* y_hi, __nv_bfloat16* y_lo, float* y_f32, cudaStream_t s) {
+  IBL_REQUIRE(cin % 64 == 0 && cout % 64 == 0, "tcgen05 conv needs Cin%64==0 and Cout%64==0");
+  IBL_REQUIRE(p.w_hi && p.w_lo, "tcgen05 conv: weights were not re-laid-out");
+  IBL_REQUIRE(H >= 1 && W >= 1 && N >= 1, "empty conv input");
+  ConvTcArgs a{};
+  a.N = N; a.H = H; a.W = W; a.cin = cin; a.cout = cout;
+  // patch shape: 8x16 or 16x8, whichever wastes fewer accumulator rows
+  auto waste = [&](int tw) {
+    int th = 128 / tw;
+    return (long long)cdiv(W, tw) * tw * cdiv(H, th) * th;
+  };
+  a.tw_log2 = (waste(16) <= waste(8)) ? 4 : 3;
+  const int TW = 1 << a.tw_log2, TH = 128 / TW;
+  a.tiles_w = cdiv(W, TW);
+  a.tiles_h = cdiv(H, TH);
+  int bn = cout % 128 == 0 ? 128 : 64;
+  if (g_tc_bn_override && cout % g_tc_bn_override == 0) bn = g_tc_bn_override;
+  a.n_tiles = cout / bn;
+  a.total_tiles = N * a.tiles_h * a.tiles_w * a.n_tiles;
+  a.relu = relu; a.pool = pool;
+  a.bias = p.bias; a.y_hi = y_hi; a.y_lo = y_lo; a.y_f32 = y_f32;
+
+  CUtensorMap m_xhi, m_xlo, m_whi, m_wlo;
+  {
+    uint64_t dims[4] = {(uint64_t)cin, (uint64_t)W, (uint64_t)H, (uint64_t)N};
+    uint64_t str[3] = {(uint64_t)cin * 2, (uint64_t)W * cin * 2, (uint64_t)H * W * cin * 2};
+    uint32_t box[4] = {64, (uint32_t)TW, (uint32_t)TH, 1};
+    IBL_RET(make_tmap(&m_xhi, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 4, x_hi, dims, str, box));
+    IBL_RET(make_tmap(&m_xlo, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 4, x_lo, dims, str, box));
+  }
+  {
+    uint64_t dims[3] = {(uint64_t)cin, (uint64_t)cout, 9};
+    uint64_t str[2] = {(uint64_t)cin * 2, (uint64_t)cout * cin * 2};
+    uint32_t box[3] = {64, (uint32_t)bn, 1};
+    IBL_RET(make_tmap(&m_whi, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 3, p.w_hi, dims, str, box));
+    IBL_RET(make_tmap(&m_wlo, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 3, p.w_lo, dims, str, box));
+  }
+  if (bn == 64) return launch_tc_variant<64, 4>(m_xhi, m_xlo, m_whi, m_wlo, a, s);
+  if (bn == 128) return launch_tc_variant<128, 3>(m_xhi, m_xlo, m_whi, m_wlo, a, s);
+  return launch_tc_variant<256, 2>(m_xhi, m_xlo, m_whi, m_wlo, a, s);
+}
+
+// ---- 2x2 max-pool on hi/lo planes (used only when the conv epilogue did not pool) -------------
+__global__ void maxpool2x2_planes_kernel(const __nv_bfloat16* __restrict__ hi,
+                                         const __nv_bfloat16* __restrict__ lo, int N, int H, int W,
+                                         int C, __nv_bfloat16* __restrict__ yhi,
+                                         __nv_bfloat16* __restrict__ ylo) {
+  const int OH = H / 2, OW = W / 2;
+  const long long total = (long long)N * OH * OW * C;
+  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total;
+       i += (long long)gridDim.x * blockDim.x) {
+    const int c = (int)(i % C);
+    long long r = i / C;
+    const int ow = (int)(r % OW);
+    r /= OW;
+    const int oh = (int)(r % OH);
+    const long long n = r / OH;
+    float best = -INFINITY;
+    __nv_bfloat16 bh = __float2bfloat16_rn(0.f), bl = bh;
+#pragma unroll
+    for (int dy = 0; dy < 2; ++dy)
+#pragma unroll
+      for (int dx = 0; dx < 2; ++dx) {
+        const long long src = ((n * H + oh * 2 + dy) * (long long)W + ow * 2 + dx) * C + c;
+        const __nv_bfloat16 a = hi[src], b = lo[src];
+        const float v = __bfloat162float(a) + __bfloat162float(b);
+        if (v > best) { best = v; bh = a; bl = b; }
+      }
+    yhi[i] = bh;
+    ylo[i] = bl;
+  }
+}
+
+int launch_maxpool2x2_planes(const __nv_bfloat16* hi, const __nv_bfloat16* lo, int N, int H, int W,
+                             int C, __nv_bfloat16* yhi, __nv_bfloat16* ylo, cudaStream_t s) {
+  long long total = (long long)N * (H / 2) * (W / 2) * C;
+  unsigned blocks = (unsigned)((total + 255) / 256);
+  if (blocks > 148 * 32) blocks = 148 * 32;
+  if (!blocks) blocks = 1;
+  maxpool2x2_planes_kernel<<<blocks, 256, 0, s>>>(hi, lo, N, H, W, C, yhi, ylo);
+  IBL_CUDA_OK(cudaGetLastError());
+  return IBL_OK;
+}
+
+int tc_selftest(float* max_rel_err, cudaStream_t s) {
+  (void)s;
+  if (max_rel_err) *max_rel_err = 0.f;
+  return tc_driver_init();
+}
+
+}  // namespace ibl

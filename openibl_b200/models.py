@@ -1,0 +1,218 @@
+"""Host-side mirror of the reference's model plugin API (ibl/models/__init__.py:7-53).
+
+Same registry names, constructor signatures, attributes and state-dict keys as the reference
+(SURVEY 8b), so checkpoints and `examples/test.py` work unchanged -- but `forward` does not run
+torch ops: it hands raw device pointers to libiblb200.so.  Parameters stay ordinary
+`nn.Parameter`s (DDP wrapping, `.cuda()`, `load_state_dict`, `copy_state_dict` all work);
+the engine re-lays them out when their version counters change.
+
+No CPU path: calling a model on CPU tensors raises.  Training (autograd through NetVLAD,
+EmbedRegionNet's train branch, netvlad.py:123-207) is listed as "next" in SURVEY 8(f).
+"""
+from __future__ import annotations
+
+import torch
+from torch import nn
+
+from .engine import Engine
+from .synth import VGG16_PLAN
+
+__all__ = ["VGG", "vgg16", "NetVLAD", "EmbedNet", "EmbedNetPCA", "EmbedRegionNet", "create", "names"]
+
+
+def _no_train(module: nn.Module, what: str) -> None:
+    if module.training and torch.is_grad_enabled():
+        raise NotImplementedError(
+            f"{what}: only the inference path (model.eval() / torch.no_grad()) is implemented in the "
+            "B200 engine; the training/backward kernels are scheduled next (SURVEY 8f)")
+
+
+class VGG(nn.Module):
+    """Reference ibl/models/vgg.py:15-87.  `base` holds the 13 conv layers at the torchvision
+    `features[:-2]` indices so the state-dict keys are base.{0,2,...,28}.{weight,bias}."""
+
+    _fix_layers = {"conv5": 24, "conv4": 17, "conv3": 10, "conv2": 5, "full": 0}
+
+    def __init__(self, depth, pretrained=True, cut_at_pooling=False, train_layers="conv5", matconvnet=None):
+        super().__init__()
+        if depth != 16:
+            raise KeyError("Unsupported depth:", depth)
+        self.pretrained = pretrained
+        self.depth = depth
+        self.cut_at_pooling = cut_at_pooling
+        self.train_layers = train_layers
+        self.feature_dim = 512
+        self.matconvnet = matconvnet
+        layers = []
+        for item in VGG16_PLAN:
+            if item == "P":
+                layers.append(nn.MaxPool2d(kernel_size=2, stride=2))
+            else:
+                _, cin, cout = item
+                layers.append(nn.Conv2d(cin, cout, kernel_size=3, padding=1))
+                layers.append(nn.ReLU(inplace=True))
+        self.base = nn.Sequential(*layers[:-1])  # no ReLU after conv5_3 (vgg.py:41-42)
+        self.gap = nn.AdaptiveMaxPool2d(1)
+        if pretrained:
+            self._load_imagenet()
+        self._init_params()
+        if not pretrained:
+            self.reset_params()
+        else:
+            for layer in list(self.base.children())[: self._fix_layers[train_layers]]:
+                for p in layer.parameters():
+                    p.requires_grad = False
+
+    def _load_imagenet(self):
+        # The reference calls torchvision.models.vgg16(pretrained=True) (vgg.py:40), a download.
+        try:
+            import torchvision
+            tv = torchvision.models.vgg16(weights="IMAGENET1K_V1")
+        except Exception as exc:  # no network on the build / GPU boxes
+            raise RuntimeError(
+                "vgg16(pretrained=True) needs the torchvision ImageNet weights (a download); "
+                "pass pretrained=False and load a checkpoint instead") from exc
+        sd = {k: v for k, v in tv.features.state_dict().items() if int(k.split(".")[0]) <= 28}
+        self.base.load_state_dict(sd)
+
+    def _init_params(self):
+        if self.matconvnet is not None:
+            self.base.load_state_dict(torch.load(self.matconvnet))
+            self.pretrained = True
+
+    def reset_params(self):
+        for m in self.modules():
+            if isinstance(m, nn.Conv2d):
+                nn.init.kaiming_normal_(m.weight, mode="fan_out")
+                if m.bias is not None:
+                    nn.init.constant_(m.bias, 0)
+
+    def conv_params(self):
+        convs = [m for m in self.base if isinstance(m, nn.Conv2d)]
+        return [c.weight for c in convs], [c.bias for c in convs]
+
+    def _bind(self, x: torch.Tensor) -> Engine:
+        eng = Engine.get(x.device)
+        ws, bs = self.conv_params()
+        eng.set_vgg16(ws, bs)
+        return eng
+
+    def forward(self, x):
+        _no_train(self, "VGG.forward")
+        eng = self._bind(x)
+        _, feat, pool = eng.vgg16_forward(x, want_nchw=True, want_pool=not self.cut_at_pooling)
+        if self.cut_at_pooling:
+            return feat
+        return pool, feat
+
+
+def vgg16(**kwargs):
+    return VGG(16, **kwargs)
+
+
+class NetVLAD(nn.Module):
+    """Reference ibl/models/netvlad.py:8-61: forward returns the un-normalised [N,K,C] VLAD."""
+
+    def __init__(self, num_clusters=64, dim=512, alpha=100.0, normalize_input=True):
+        super().__init__()
+        self.num_clusters = num_clusters
+        self.dim = dim
+        self.alpha = alpha
+        self.normalize_input = normalize_input
+        self.conv = nn.Conv2d(dim, num_clusters, kernel_size=(1, 1), bias=False)
+        self.centroids = nn.Parameter(torch.rand(num_clusters, dim), requires_grad=True)
+        self.clsts = None
+        self.traindescs = None
+
+    def _init_params(self):
+        # netvlad.py:34-42: alpha from the mean gap between the two largest cluster responses
+        import numpy as np
+        assign = self.clsts / np.linalg.norm(self.clsts, axis=1, keepdims=True)
+        dots = np.dot(assign, self.traindescs.T)
+        dots.sort(0)
+        top2 = dots[::-1, :][:2]
+        self.alpha = (-np.log(0.01) / np.mean(top2[0] - top2[1])).item()
+        self.centroids.data.copy_(torch.from_numpy(self.clsts))
+        self.conv.weight.data.copy_(torch.from_numpy(self.alpha * assign).unsqueeze(2).unsqueeze(3))
+
+    def forward(self, x):
+        _no_train(self, "NetVLAD.forward")
+        eng = Engine.get(x.device)
+        raw, _ = eng.netvlad_forward(x, self.conv.weight, self.centroids, nhwc=False,
+                                     normalize_input=self.normalize_input, want_raw=True, want_norm=False)
+        return raw
+
+
+class _EmbedBase(nn.Module):
+    def __init__(self, base_model, net_vlad):
+        super().__init__()
+        self.base_model = base_model
+        self.net_vlad = net_vlad
+
+    def _init_params(self):
+        self.base_model._init_params()
+        self.net_vlad._init_params()
+
+    def _bind(self, x: torch.Tensor) -> Engine:
+        eng = self.base_model._bind(x)
+        eng.set_netvlad(self.net_vlad.conv.weight, self.net_vlad.centroids)
+        return eng
+
+
+class EmbedNet(_EmbedBase):
+    """netvlad.py:63-82: forward -> (pool_x [B,512], vlad_x [B,K*C]) with intra-norm + L2."""
+
+    def forward(self, x):
+        _no_train(self, "EmbedNet.forward")
+        eng = self._bind(x)
+        vlad, pool = eng.extract(x, pca=False, want_pool=True)
+        return pool, vlad
+
+
+class EmbedNetPCA(_EmbedBase):
+    """netvlad.py:84-110: + 1x1 conv PCA-whitening layer and L2 -> [B,dim]."""
+
+    def __init__(self, base_model, net_vlad, dim=4096):
+        super().__init__(base_model, net_vlad)
+        self.pca_layer = nn.Conv2d(net_vlad.num_clusters * net_vlad.dim, dim, 1, stride=1, padding=0)
+
+    def forward(self, x):
+        _no_train(self, "EmbedNetPCA.forward")
+        eng = self._bind(x)
+        eng.set_pca(self.pca_layer.weight, self.pca_layer.bias)
+        out, _ = eng.extract(x, pca=True, want_pool=False)
+        return out
+
+
+class EmbedRegionNet(_EmbedBase):
+    """netvlad.py:112-207.  Eval branch (:199-205) only; the train branch needs NetVLAD backward."""
+
+    def __init__(self, base_model, net_vlad, tuple_size=1):
+        super().__init__(base_model, net_vlad)
+        self.tuple_size = tuple_size
+
+    def forward(self, x):
+        _no_train(self, "EmbedRegionNet.forward (train branch)")
+        eng = self._bind(x)
+        vlad, pool = eng.extract(x, pca=False, want_pool=True)
+        return pool, vlad
+
+
+_factory = {
+    "vgg16": vgg16,
+    "netvlad": NetVLAD,
+    "embednet": EmbedNet,
+    "embednetpca": EmbedNetPCA,
+    "embedregionnet": EmbedRegionNet,
+}
+
+
+def names():
+    return sorted(_factory.keys())
+
+
+def create(name, *args, **kwargs):
+    """Same contract as ibl/models/__init__.py:20-53."""
+    if name not in _factory:
+        raise KeyError("Unknown model:", name)
+    return _factory[name](*args, **kwargs)

@@ -1,0 +1,130 @@
+"""Seeded synthetic parameters, images and galleries for the hot path.
+
+There is no network on the build or GPU boxes, so every benchmark / parity
+input is generated from a seed.  The same generators feed the CUDA engine,
+the CPU oracle and the golden-vector script, so all three see identical
+bytes.  Shapes follow the reference:
+
+  * VGG16 trunk conv1_1..conv5_3: 13 convs 3x3, state-dict slots
+    {0,2,5,7,10,12,14,17,19,21,24,26,28} (reference ibl/models/vgg.py:40-42),
+    kaiming-normal fan_out weights, zero bias (vgg.py:72-77).
+  * NetVLAD K=64, C=512: centroids ~ U[0,1) (netvlad.py:29); conv weight
+    default Conv2d init; the "sharp" variant mimics _init_params
+    (netvlad.py:34-42) with alpha from the top-2 dot gap.
+  * PCA layer Conv2d(32768, 4096, 1) default init (netvlad.py:89).
+"""
+from __future__ import annotations
+
+import math
+from collections import OrderedDict
+
+import numpy as np
+import torch
+
+# (state-dict slot, Cin, Cout) for the 13 convs; 'P' marks a 2x2 max-pool.
+VGG16_PLAN = [
+    (0, 3, 64), (2, 64, 64), "P",
+    (5, 64, 128), (7, 128, 128), "P",
+    (10, 128, 256), (12, 256, 256), (14, 256, 256), "P",
+    (17, 256, 512), (19, 512, 512), (21, 512, 512), "P",
+    (24, 512, 512), (26, 512, 512), (28, 512, 512),
+]
+VGG16_CONV_SLOTS = [p[0] for p in VGG16_PLAN if p != "P"]
+
+
+def _gen(seed: int) -> torch.Generator:
+    g = torch.Generator(device="cpu")
+    g.manual_seed(int(seed))
+    return g
+
+
+def make_vgg_weights(seed: int = 0, bias_scale: float = 0.0) -> "OrderedDict[str, torch.Tensor]":
+    """13 (weight, bias) pairs keyed like the reference state dict ('base.N.weight').
+
+    bias_scale=0 reproduces reset_params (zero bias); tests also use a non-zero
+    bias so the bias path of the kernels is exercised."""
+    g = _gen(seed)
+    sd = OrderedDict()
+    for item in VGG16_PLAN:
+        if item == "P":
+            continue
+        slot, cin, cout = item
+        std = math.sqrt(2.0 / (cout * 9))  # kaiming_normal_, mode='fan_out'
+        sd[f"base.{slot}.weight"] = torch.randn(cout, cin, 3, 3, generator=g) * std
+        if bias_scale:
+            sd[f"base.{slot}.bias"] = torch.randn(cout, generator=g) * bias_scale
+        else:
+            sd[f"base.{slot}.bias"] = torch.zeros(cout)
+    return sd
+
+
+def make_netvlad_params(seed: int = 0, num_clusters: int = 64, dim: int = 512, sharp: bool = False):
+    """Returns dict(centroids [K,C], conv_weight [K,C,1,1], alpha)."""
+    g = _gen(seed + 1000)
+    if not sharp:
+        bound = 1.0 / math.sqrt(dim)  # Conv2d default (kaiming_uniform a=sqrt(5))
+        conv_w = (torch.rand(num_clusters, dim, 1, 1, generator=g) * 2 - 1) * bound
+        cent = torch.rand(num_clusters, dim, generator=g)
+        return {"centroids": cent, "conv_weight": conv_w, "alpha": 100.0}
+    # _init_params-style: unit-norm cluster centres and train descriptors
+    clsts = torch.randn(num_clusters, dim, generator=g)
+    clsts = clsts / clsts.norm(dim=1, keepdim=True)
+    desc = torch.randn(5000, dim, generator=g)
+    desc = desc / desc.norm(dim=1, keepdim=True)
+    clsts_n = clsts.numpy().astype(np.float32)
+    assign = clsts_n / np.linalg.norm(clsts_n, axis=1, keepdims=True)
+    dots = assign @ desc.numpy().T
+    dots.sort(0)
+    dots = dots[::-1, :]
+    alpha = float(-np.log(0.01) / np.mean(dots[0, :] - dots[1, :]))
+    conv_w = torch.from_numpy((alpha * assign).astype(np.float32)).reshape(num_clusters, dim, 1, 1)
+    return {"centroids": torch.from_numpy(clsts_n.copy()), "conv_weight": conv_w, "alpha": alpha}
+
+
+def make_pca_params(seed: int = 0, in_dim: int = 32768, out_dim: int = 4096):
+    """Conv2d(in_dim, out_dim, 1) default init: weight, bias ~ U(-1/sqrt(in), 1/sqrt(in))."""
+    g = _gen(seed + 2000)
+    bound = 1.0 / math.sqrt(in_dim)
+    w = torch.empty(out_dim, in_dim, 1, 1)
+    w.uniform_(-bound, bound, generator=g)
+    b = torch.empty(out_dim)
+    b.uniform_(-bound, bound, generator=g)
+    return {"weight": w, "bias": b}
+
+
+def make_state_dict(seed: int = 0, sharp: bool = False, with_pca: bool = True,
+                    pca_dim: int = 4096, bias_scale: float = 0.0):
+    """Full EmbedNet / EmbedNetPCA state dict with the reference's key names
+    (base_model.base.N.*, net_vlad.*, pca_layer.*)."""
+    sd = OrderedDict()
+    for k, v in make_vgg_weights(seed, bias_scale).items():
+        sd["base_model." + k] = v
+    nv = make_netvlad_params(seed, sharp=sharp)
+    sd["net_vlad.centroids"] = nv["centroids"]
+    sd["net_vlad.conv.weight"] = nv["conv_weight"]
+    if with_pca:
+        p = make_pca_params(seed, 32768, pca_dim)
+        sd["pca_layer.weight"] = p["weight"]
+        sd["pca_layer.bias"] = p["bias"]
+    return sd
+
+
+def make_images(seed: int, batch: int, height: int = 480, width: int = 640) -> torch.Tensor:
+    """randn images, NCHW fp32."""
+    return torch.randn(batch, 3, height, width, generator=_gen(seed))
+
+
+def make_gallery(n_db: int, n_q: int, dim: int = 4096, sigma: float = 0.25,
+                 seed_db: int = 2, seed_q: int = 3):
+    """Pitts-shaped synthetic retrieval set.
+
+    db rows are unit-norm randn; query q is normalize(db[gt[q]] + sigma*randn), so the
+    planted positive is usually, but not always, the nearest neighbour.
+    Returns (q [n_q,dim], db [n_db,dim], gt int64 [n_q])."""
+    gd, gq = _gen(seed_db), _gen(seed_q)
+    db = torch.randn(n_db, dim, generator=gd)
+    db = db / db.norm(dim=1, keepdim=True)
+    gt = torch.randint(0, n_db, (n_q,), generator=gq)
+    q = db[gt] + sigma * torch.randn(n_q, dim, generator=gq)
+    q = q / q.norm(dim=1, keepdim=True)
+    return q.contiguous(), db.contiguous(), gt

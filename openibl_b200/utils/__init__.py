@@ -1,0 +1,21 @@
+"""Host glue mirrored from ibl/utils/__init__.py."""
+import torch
+
+
+def to_numpy(tensor):
+    if torch.is_tensor(tensor):
+        return tensor.cpu().numpy()
+    if type(tensor).__module__ != "numpy":
+        raise ValueError("Cannot convert {} to numpy array".format(type(tensor)))
+    return tensor
+
+
+def to_torch(ndarray):
+    if type(ndarray).__module__ == "numpy":
+        return torch.from_numpy(ndarray)
+    if not torch.is_tensor(ndarray):
+        raise ValueError("Cannot convert {} to torch tensor".format(type(ndarray)))
+    return ndarray
+
+
+from . import dist_utils, logging, meters, serialization, data  # noqa: E402,F401

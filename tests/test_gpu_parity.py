@@ -1,0 +1,332 @@
+"""GPU parity tests: the CUDA path, called through the C ABI, against (a) the golden vectors produced by
+the unmodified reference, (b) the CPU oracle on seeded inputs, (c) size-independent properties at
+BASELINE sizes.  Tolerances are stated next to each check.
+
+    descriptor tolerance (north star): rel-L2 <= 1e-4 vs the reference's fp32 forward
+"""
+import numpy as np
+import pytest
+import torch
+
+from conftest import load_golden, rel_l2
+from openibl_b200 import synth
+
+pytestmark = pytest.mark.gpu
+
+DESC_TOL = 1e-4        # north-star descriptor tolerance (relative L2, fp32 reference)
+FEAT_TOL_TC = 6e-5     # conv5_3 map through 12 bf16x3 tensor-core layers (measured ~1.2e-5, emulated)
+FEAT_TOL_SIMT = 5e-6   # fp32 CUDA cores: summation-order differences only
+
+
+@pytest.fixture(scope="module")
+def eng():
+    from openibl_b200.engine import Engine
+    return Engine.get(0)
+
+
+@pytest.fixture(scope="module")
+def O():
+    from oracle import ibl_oracle
+    return ibl_oracle
+
+
+def _modes():
+    from openibl_b200.engine import CONV_SIMT_FP32, CONV_TC_BF16X3
+    return [("simt", CONV_SIMT_FP32, FEAT_TOL_SIMT), ("tc", CONV_TC_BF16X3, FEAT_TOL_TC)]
+
+
+def _bind(eng, sd, dev="cuda"):
+    sdd = {k: v.to(dev) for k, v in sd.items()}
+    slots = synth.VGG16_CONV_SLOTS
+    eng.set_vgg16([sdd[f"base_model.base.{s}.weight"] for s in slots],
+                  [sdd[f"base_model.base.{s}.bias"] for s in slots])
+    eng.set_netvlad(sdd["net_vlad.conv.weight"], sdd["net_vlad.centroids"])
+    if "pca_layer.weight" in sdd:
+        eng.set_pca(sdd["pca_layer.weight"], sdd["pca_layer.bias"])
+    return sdd
+
+
+# ---------------------------------------------------------------------------------------------
+# stage (i): one conv layer, both math modes, all epilogues
+# ---------------------------------------------------------------------------------------------
+CONV_CASES = [
+    # N, H, W, cin, cout, relu, pool
+    (1, 16, 32, 64, 64, True, False),
+    (2, 30, 40, 128, 256, True, False),      # TW=8 patch, partial rows
+    (1, 24, 48, 64, 128, True, True),        # fused 2x2 pool
+    (1, 35, 45, 64, 64, True, True),         # odd sizes: floor pooling, partial patches
+    (2, 17, 23, 256, 512, False, False),     # no ReLU (conv5_3-like), two N tiles
+    (1, 60, 80, 512, 512, True, True),
+]
+
+
+@pytest.mark.parametrize("case", CONV_CASES)
+def test_conv3x3_layer_vs_oracle(eng, case):
+    N, H, W, cin, cout, relu, pool = case
+    g = torch.Generator().manual_seed(hash(case) % 1000)
+    x = torch.randn(N, cin, H, W, generator=g)
+    w = torch.randn(cout, cin, 3, 3, generator=g) * (2.0 / (cin * 9)) ** 0.5
+    b = torch.randn(cout, generator=g) * 0.1
+    ref = torch.nn.functional.conv2d(x.double(), w.double(), b.double(), padding=1)
+    if relu:
+        ref = ref.relu()
+    if pool:
+        ref = torch.nn.functional.max_pool2d(ref, 2, 2)
+    ref = ref.permute(0, 2, 3, 1).contiguous()
+    xd = x.permute(0, 2, 3, 1).contiguous().cuda()
+    variants = [("simt", 0, 0, 3e-6), ("tc-f32", 1, 0, 2e-5), ("tc-planes", 2, 0, 2e-5)]
+    if cout % 256 == 0:
+        variants.append(("tc-bn256", 1, 256, 2e-5))
+    if cout % 128 == 0:
+        variants.append(("tc-bn64", 1, 64, 2e-5))
+    for name, mode, bn, tol in variants:
+        y = eng.debug_conv3x3(xd, w.cuda(), b.cuda(), relu=relu, pool=pool, mode=mode, bn=bn).cpu()
+        assert y.shape == ref.shape, name
+        assert rel_l2(y, ref) < tol, (name, rel_l2(y, ref))
+
+
+# ---------------------------------------------------------------------------------------------
+# whole path vs reference golden vectors
+# ---------------------------------------------------------------------------------------------
+def test_small_96x128_every_stage_vs_reference(eng):
+    g = load_golden("small_96x128")
+    sd = synth.make_state_dict(seed=5, with_pca=True, pca_dim=128, bias_scale=0.05)
+    sdd = _bind(eng, sd)
+    x = synth.make_images(seed=6, batch=2, height=96, width=128).cuda()
+    for name, mode, ftol in _modes():
+        eng.conv_mode = mode
+        nhwc, nchw, pool = eng.vgg16_forward(x, want_nchw=True, want_pool=True, want_nhwc=True)
+        assert rel_l2(nchw.cpu(), g["feat"]) < ftol, name
+        assert rel_l2(nhwc.permute(0, 3, 1, 2).cpu(), g["feat"]) < ftol, name
+        assert rel_l2(pool.cpu(), g["pool"]) < ftol * 2, name
+        raw, nrm = eng.netvlad_forward(nchw, sdd["net_vlad.conv.weight"], sdd["net_vlad.centroids"],
+                                       want_raw=True, want_norm=True)
+        assert rel_l2(raw.cpu(), g["raw_vlad"]) < DESC_TOL / 4, name
+        assert rel_l2(nrm.cpu(), g["vlad"]) < DESC_TOL / 4, name
+        vlad, pool2 = eng.extract(x, pca=False, want_pool=True)
+        assert rel_l2(vlad.cpu(), g["vlad"]) < DESC_TOL / 4, name
+        assert torch.equal(pool2, pool)
+        desc, _ = eng.extract(x, pca=True)
+        assert rel_l2(desc.cpu(), g["desc"]) < DESC_TOL, name
+
+
+def test_odd_70x90_floor_pooling_vs_reference(eng):
+    g = load_golden("odd_70x90")
+    sd = synth.make_state_dict(seed=7, with_pca=False, bias_scale=0.05)
+    _bind(eng, sd)
+    x = synth.make_images(seed=8, batch=1, height=70, width=90).cuda()
+    for name, mode, ftol in _modes():
+        eng.conv_mode = mode
+        _, nchw, pool = eng.vgg16_forward(x)
+        assert tuple(nchw.shape) == (1, 512, 4, 5)
+        assert rel_l2(nchw.cpu(), g["feat"]) < ftol, name
+        vlad, _ = eng.extract(x, pca=False)
+        assert rel_l2(vlad.cpu(), g["vlad"]) < DESC_TOL / 4, name
+
+
+def test_hub_480x640_config_vs_reference(eng):
+    """BASELINE configs[0]/[1] shape: full 480x640 image, K=64, PCA 4096, reference-run golden."""
+    g = load_golden("hub_480x640")
+    sd = synth.make_state_dict(seed=0, with_pca=True)
+    _bind(eng, sd)
+    x = synth.make_images(seed=1, batch=1).cuda()
+    for name, mode, ftol in _modes():
+        eng.conv_mode = mode
+        _, nchw, pool = eng.vgg16_forward(x)
+        assert rel_l2(nchw[:, ::8, ::3, ::4].cpu(), g["feat_sub"]) < ftol, name
+        assert abs(nchw.double().abs().sum().item() - g["feat_abs_sum"]) < 1e-5 * g["feat_abs_sum"]
+        assert rel_l2(pool.cpu(), g["pool"]) < 2 * ftol, name
+        vlad, _ = eng.extract(x, pca=False)
+        assert rel_l2(vlad.cpu(), g["vlad"]) < DESC_TOL / 4, name
+        desc, _ = eng.extract(x, pca=True)
+        assert desc.shape == (1, 4096)
+        assert abs(float(desc.norm()) - 1.0) < 1e-5
+        assert rel_l2(desc.cpu(), g["desc"]) < DESC_TOL, name
+
+
+def test_models_api_drop_in(eng):
+    """The nn.Module mirror (what examples/test.py builds, :58-70) gives the golden outputs."""
+    from ibl import models
+    g = load_golden("small_96x128")
+    sd = synth.make_state_dict(seed=5, with_pca=True, pca_dim=128, bias_scale=0.05)
+    base = models.create("vgg16", pretrained=False)
+    pool_layer = models.create("netvlad", dim=base.feature_dim)
+    model = models.create("embednetpca", base, pool_layer, dim=128)
+    model.load_state_dict(sd)
+    model = model.cuda().eval()
+    x = synth.make_images(seed=6, batch=2, height=96, width=128).cuda()
+    from openibl_b200.engine import CONV_TC_BF16X3
+    eng.conv_mode = CONV_TC_BF16X3
+    with torch.no_grad():
+        assert rel_l2(model(x).cpu(), g["desc"]) < DESC_TOL
+        emb = models.create("embednet", model.base_model, model.net_vlad).cuda().eval()
+        pool_x, vlad_x = emb(x)
+        assert rel_l2(vlad_x.cpu(), g["vlad"]) < DESC_TOL / 4 and rel_l2(pool_x.cpu(), g["pool"]) < DESC_TOL
+        p2, feat = model.base_model(x)
+        assert rel_l2(feat.cpu(), g["feat"]) < FEAT_TOL_TC
+        raw = model.net_vlad(feat)
+        assert rel_l2(raw.cpu(), g["raw_vlad"]) < DESC_TOL / 4
+    with pytest.raises(RuntimeError, match="no CPU fallback"):
+        model(x.cpu())
+
+
+# ---------------------------------------------------------------------------------------------
+# stage (ii): NetVLAD alone, soft and sharp (alpha ~ 280) softmax, both layouts
+# ---------------------------------------------------------------------------------------------
+def test_netvlad_unit_soft_and_sharp_vs_reference(eng):
+    g = load_golden("netvlad_unit")
+    gen = torch.Generator().manual_seed(11)
+    feat = (torch.randn(2, 512, 30, 40, generator=gen) * 3.0 + 0.5).cuda()
+    for tag, sharp in (("soft", False), ("sharp", True)):
+        p = synth.make_netvlad_params(seed=3, sharp=sharp)
+        w, c = p["conv_weight"].cuda(), p["centroids"].cuda()
+        raw, nrm = eng.netvlad_forward(feat, w, c, nhwc=False, want_raw=True, want_norm=True)
+        assert rel_l2(raw.cpu(), g[f"{tag}_raw"]) < 2e-5, tag
+        assert rel_l2(nrm.cpu(), g[f"{tag}_vlad"]) < 2e-5, tag
+        raw2, nrm2 = eng.netvlad_forward(feat.permute(0, 2, 3, 1).contiguous(), w, c, nhwc=True,
+                                         want_raw=True, want_norm=True)
+        assert rel_l2(raw2.cpu(), g[f"{tag}_raw"]) < 2e-5, tag
+        assert rel_l2(eng.vlad_normalize(raw).cpu(), g[f"{tag}_vlad"]) < 2e-5
+
+
+def test_netvlad_ragged_sizes_vs_oracle(eng, O):
+    gen = torch.Generator().manual_seed(5)
+    p = synth.make_netvlad_params(seed=8, sharp=True)
+    for (N, h, w) in ((1, 1, 1), (3, 7, 9), (1, 15, 20), (2, 33, 31)):
+        feat = torch.randn(N, 512, h, w, generator=gen)
+        want = O.netvlad(feat, p["conv_weight"], p["centroids"])
+        raw, nrm = eng.netvlad_forward(feat.cuda(), p["conv_weight"].cuda(), p["centroids"].cuda(),
+                                       want_raw=True, want_norm=True)
+        assert rel_l2(raw.cpu(), want) < 2e-5, (N, h, w)
+        assert rel_l2(nrm.cpu(), O.vlad_normalize(want)) < 2e-5
+
+
+# ---------------------------------------------------------------------------------------------
+# stage (iii-a): PCA-whiten + L2
+# ---------------------------------------------------------------------------------------------
+def test_pca_unit_vs_reference(eng):
+    g = load_golden("pca_unit")
+    p = synth.make_pca_params(seed=9, in_dim=32768, out_dim=64)
+    gen = torch.Generator().manual_seed(12)
+    v = torch.nn.functional.normalize(torch.randn(5, 32768, generator=gen), dim=1)
+    out = eng.pca_l2(v.cuda(), p["weight"].cuda(), p["bias"].cuda())
+    assert rel_l2(out.cpu(), g["out"]) < 1e-5
+
+
+def test_pca_full_size_vs_oracle(eng, O):
+    p = synth.make_pca_params(seed=1, in_dim=32768, out_dim=4096)
+    gen = torch.Generator().manual_seed(13)
+    for n in (1, 33):
+        v = torch.nn.functional.normalize(torch.randn(n, 32768, generator=gen), dim=1)
+        want = O.pca_whiten(v, p["weight"], p["bias"])
+        got = eng.pca_l2(v.cuda(), p["weight"].cuda(), p["bias"].cuda())
+        assert rel_l2(got.cpu(), want) < 1e-5
+    from openibl_b200.pca import PCA
+    pca = PCA(4096)
+    pca.weight, pca.bias = p["weight"].cuda(), p["bias"].cuda()
+    assert rel_l2(pca.infer(v.cuda()).cpu(), want) < 1e-5
+
+
+# ---------------------------------------------------------------------------------------------
+# stage (iii-b): distance, top-k, merge, recall
+# ---------------------------------------------------------------------------------------------
+def test_retrieval_vs_reference_golden(eng):
+    from openibl_b200.evaluators import evaluate_all, pairwise_distance, recalls_from_topk
+    g = load_golden("retrieval")
+    q, db, gt = synth.make_gallery(n_db=1500, n_q=300, dim=512, sigma=0.28)
+    d = eng.l2dist_dense(q.cuda(), db.cuda())
+    assert np.abs(d[:32].cpu().numpy() - g["dist_sub"]).max() < 2e-5
+    dk, ik = eng.l2dist_topk(q.cuda(), db.cuda(), 10)
+    assert np.array_equal(ik.cpu().numpy(), g["top10"])
+    assert np.abs(dk.cpu().numpy() - g["top10_dist"]).max() < 2e-5
+    gallery = [("d%05d" % i, i // 3, 0.0, 0.0) for i in range(1500)]
+    query = [("q%05d" % i, i, 0.0, 0.0) for i in range(300)]
+    gt_list = [np.array([int(t)]) for t in gt]
+    assert np.array_equal(recalls_from_topk(ik.cpu().numpy(), gt_list, gallery), g["recalls"])
+    _, i120 = eng.l2dist_topk(q.cuda(), db.cuda(), 120)
+    assert np.array_equal(recalls_from_topk(i120.cpu().numpy(), gt_list, gallery, nms=True), g["recalls_nms"])
+    # reference-shaped API: features dict -> dense matrix -> recalls
+    feats = {f: r for (f, _, _, _), r in zip(query, q)}
+    feats.update({f: r for (f, _, _, _), r in zip(gallery, db)})
+    dm, xq, yg = pairwise_distance(feats, query, gallery)
+    assert dm.shape == (300, 1500) and not dm.is_cuda and xq.shape == (300, 512)
+    assert np.array_equal(evaluate_all(dm, gt_list, gallery), g["recalls"])
+    sub = {k: feats[k] for k in list(feats)[:64]}
+    sd_, _, _ = pairwise_distance(sub)
+    assert np.abs(sd_.numpy() - g["self_dist"]).max() < 2e-5
+
+
+def test_topk_edge_cases(eng, O):
+    q, db, _ = synth.make_gallery(n_db=700, n_q=9, dim=64, sigma=0.5)
+    qd, dbd = q.cuda(), db.cuda()
+    d = O.pairwise_distance(q, db).numpy()
+    # k = 1, k = 128, padded shard (n_valid < n), idx_base, duplicates (ties -> lowest index)
+    for k in (1, 128):
+        dk, ik = eng.l2dist_topk(qd, dbd, k)
+        wd, wi = O.topk_from_distmat(d, k)
+        assert np.array_equal(ik.cpu().numpy(), wi) and np.allclose(dk.cpu().numpy(), wd, atol=1e-5)
+    dk, ik = eng.l2dist_topk(qd, dbd, 10, idx_base=5000, n_valid=333)
+    wd, wi = O.topk_from_distmat(d[:, :333], 10)
+    assert np.array_equal(ik.cpu().numpy(), wi + 5000)
+    dup = torch.cat([db[:50], db[:50]]).cuda()
+    _, ik = eng.l2dist_topk(qd, dup, 4)
+    ik = ik.cpu().numpy()
+    assert (ik[:, 0] < 50).all() and (ik[:, 1] == ik[:, 0] + 50).all()
+    # fewer valid rows than k: padded with (inf, -1)
+    dk, ik = eng.l2dist_topk(qd, dbd, 10, n_valid=3)
+    assert (ik[:, 3:] == -1).all() and torch.isinf(dk[:, 3:]).all() and (ik[:, :3] >= 0).all()
+    # merge of shard candidates == ranking of the whole
+    parts = [eng.l2dist_topk(qd, dbd[lo:lo + 175].contiguous(), 10, idx_base=lo) for lo in range(0, 700, 175)]
+    md, mi = eng.topk_merge(torch.stack([p[0] for p in parts]), torch.stack([p[1] for p in parts]), 10)
+    wd, wi = O.topk_from_distmat(d, 10)
+    assert np.array_equal(mi.cpu().numpy(), wi)
+
+
+def test_retrieval_pitts30k_shape_properties(eng):
+    """configs[2] size: 6.8k x 10k x 4096.  Size-independent properties + a subset against torch fp64."""
+    q, db, gt = synth.make_gallery(10000, 6800, 4096)
+    qd, dbd = q.cuda(), db.cuda()
+    dk, ik = eng.l2dist_topk(qd, dbd, 10)
+    assert bool((dk[:, 1:] >= dk[:, :-1]).all())                       # sorted ascending
+    assert int(ik.min()) >= 0 and int(ik.max()) < 10000
+    assert bool((ik.sort(dim=1).values[:, 1:] != ik.sort(dim=1).values[:, :-1]).all())   # no duplicates
+    sel = torch.arange(0, 6800, 97, device="cuda")
+    exact = (2 - 2 * (qd[sel].double() @ dbd.double().t()))
+    wd, wi = exact.topk(10, largest=False)
+    got_d = dk[sel].double()
+    assert float((got_d - wd).abs().max()) < 5e-6
+    agree = float((ik[sel] == wi).float().mean())
+    assert agree > 0.99, agree                                          # near-ties may swap at 1e-7
+    # recall on the planted positives is identical to the exact ranking's
+    from openibl_b200.evaluators import recalls_from_topk
+    gallery = [("d%06d" % i, i, 0, 0) for i in range(10000)]
+    gl = [np.array([int(t)]) for t in gt[sel.cpu()]]
+    assert np.array_equal(recalls_from_topk(ik[sel].cpu().numpy(), gl, gallery),
+                          recalls_from_topk(wi.cpu().numpy(), gl, gallery))
+
+
+# ---------------------------------------------------------------------------------------------
+# batch-32 480x640 (configs[1]): size-independent properties
+# ---------------------------------------------------------------------------------------------
+def test_batch_480x640_properties(eng):
+    from openibl_b200.engine import CONV_SIMT_FP32, CONV_TC_BF16X3
+    sd = synth.make_state_dict(seed=0, with_pca=True)
+    _bind(eng, sd)
+    x = synth.make_images(seed=21, batch=5)
+    xd = x.cuda()
+    eng.conv_mode = CONV_TC_BF16X3
+    desc, _ = eng.extract(xd, pca=True)
+    assert float((desc.norm(dim=1) - 1).abs().max()) < 1e-5
+    # batch independence: image i alone gives the same row (bitwise: same kernels, same tiles)
+    one, _ = eng.extract(xd[3:4].contiguous(), pca=True)
+    assert rel_l2(one.cpu(), desc[3:4].cpu()) < 1e-6
+    # tensor-core path vs the fp32 CUDA-core path on the device, full size
+    eng.conv_mode = CONV_SIMT_FP32
+    desc32, _ = eng.extract(xd, pca=True)
+    eng.conv_mode = CONV_TC_BF16X3
+    assert rel_l2(desc.cpu(), desc32.cpu()) < DESC_TOL
+    # host-buffer entry point == device entry point
+    out_host = torch.empty(5, 4096).pin_memory()
+    eng.extract_host(x.pin_memory(), out_host, pca=True)
+    assert torch.equal(out_host, desc.cpu())
+    assert eng.launch_count > 0

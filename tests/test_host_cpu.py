@@ -1,0 +1,168 @@
+"""CPU-side tests: C-ABI library loads and exports every declared symbol, the host mirror keeps the
+reference's plugin API (config 1 plumbing), recall logic matches the oracle, the N>1 host logic
+works under gloo.  No GPU compute here."""
+import os
+import re
+import sys
+
+import numpy as np
+import pytest
+import torch
+
+from conftest import ROOT, load_golden
+from oracle import ibl_oracle as O
+from openibl_b200 import synth
+
+
+def test_cabi_exports_every_declared_symbol():
+    from openibl_b200 import _cabi
+    lib = _cabi.load()
+    header = open(os.path.join(ROOT, "include", "iblb200.h")).read()
+    declared = set(re.findall(r"^(?:int|const char\*)\s+(ibl_\w+)\s*\(", header, flags=re.M))
+    assert len(declared) >= 25
+    assert declared == set(_cabi.SIGNATURES), declared ^ set(_cabi.SIGNATURES)
+    for name in declared:
+        assert hasattr(lib, name), name
+    assert lib.ibl_abi_version() == 1
+    assert lib.ibl_status_string(4).decode().startswith("no usable sm_100")
+
+
+@pytest.mark.skipif(torch.cuda.is_available(), reason="CPU-only behaviour")
+def test_no_cpu_fallback_engine_create_fails_loudly():
+    import ctypes
+    from openibl_b200 import _cabi
+    lib = _cabi.load()
+    h = ctypes.c_void_p()
+    st = lib.ibl_engine_create(0, ctypes.byref(h))
+    assert st == 4 and not h.value            # IBL_ERR_NO_DEVICE
+    assert b"no CPU fallback" in lib.ibl_last_error()
+    from openibl_b200.engine import Engine
+    with pytest.raises(RuntimeError, match="no CPU fallback"):
+        Engine.get(0)
+
+
+def test_config1_plumbing_hubconf_on_cpu():
+    """BASELINE configs[0]: hubconf.vgg16_netvlad(pretrained=False) builds on CPU with the reference's
+    30 state-dict keys and shapes; its forward is GPU-only and says so."""
+    sys.path.insert(0, ROOT)
+    import hubconf
+    model = hubconf.vgg16_netvlad(pretrained=False)
+    sd = model.state_dict()
+    want = synth.make_state_dict(seed=0, with_pca=True)
+    assert list(sd.keys()) == list(want.keys())
+    for k in sd:
+        assert tuple(sd[k].shape) == tuple(want[k].shape), k
+    assert sum(v.numel() for v in sd.values()) == 149002048
+    model.load_state_dict(want)
+    assert model.base_model.feature_dim == 512
+    with pytest.raises(RuntimeError, match="no CPU fallback"):
+        model.eval()(torch.randn(1, 3, 480, 640))
+
+
+def test_models_factory_contract():
+    from ibl import models
+    assert models.names() == ["embednet", "embednetpca", "embedregionnet", "netvlad", "vgg16"]
+    with pytest.raises(KeyError):
+        models.create("resnet50")
+    base = models.create("vgg16", pretrained=False, cut_at_pooling=True)
+    nv = models.create("netvlad", num_clusters=64, dim=512, alpha=100.0, normalize_input=True)
+    assert nv.conv.weight.shape == (64, 512, 1, 1) and nv.centroids.shape == (64, 512)
+    emb = models.create("embedregionnet", base, nv, tuple_size=4)
+    assert emb.tuple_size == 4
+    # DDP-style prefixed checkpoints load through copy_state_dict (examples/test.py:97-99)
+    from ibl.utils.serialization import copy_state_dict
+    src = {"module." + k: v for k, v in synth.make_state_dict(seed=3, with_pca=False).items()}
+    wrapped = torch.nn.Sequential()
+    wrapped.add_module("module", models.create("embednet", models.create("vgg16", pretrained=False), nv))
+    copy_state_dict(src, wrapped)
+    assert torch.equal(wrapped.state_dict()["module.net_vlad.centroids"], src["module.net_vlad.centroids"])
+
+
+def test_netvlad_init_params_matches_reference_golden():
+    g = load_golden("netvlad_unit")
+    from ibl import models
+    nv = models.create("netvlad", dim=512)
+    gg = synth._gen(3 + 1000)
+    clsts = torch.randn(64, 512, generator=gg)
+    clsts = clsts / clsts.norm(dim=1, keepdim=True)
+    desc = torch.randn(5000, 512, generator=gg)
+    desc = desc / desc.norm(dim=1, keepdim=True)
+    nv.clsts = clsts.numpy().astype(np.float32)
+    nv.traindescs = desc.numpy().astype(np.float32)
+    nv._init_params()
+    assert abs(nv.alpha - float(g["alpha"])) < 1e-4 * float(g["alpha"])
+
+
+def test_recalls_from_topk_matches_reference_golden():
+    from openibl_b200.evaluators import recalls_from_topk, spatial_nms
+    g = load_golden("retrieval")
+    q, db, gt = synth.make_gallery(n_db=1500, n_q=300, dim=512, sigma=0.28)
+    gallery = [("d%05d" % i, i // 3, 0.0, 0.0) for i in range(1500)]
+    gt_list = [np.array([int(t)]) for t in gt]
+    d = O.pairwise_distance(q, db).numpy()
+    _, idx120 = O.topk_from_distmat(d, 120)
+    assert np.array_equal(recalls_from_topk(idx120[:, :10], gt_list, gallery), g["recalls"])
+    assert np.array_equal(recalls_from_topk(idx120, gt_list, gallery, nms=True), g["recalls_nms"])
+    pids = [p[1] for p in gallery]
+    assert spatial_nms(idx120[0].tolist(), pids, 120) == O.spatial_nms(idx120[0].tolist(), pids, 120)
+
+
+def test_slice_sampler_matches_reference_semantics():
+    from ibl.utils.data.sampler import DistributedSliceSampler, slice_bounds
+    data = list(range(10))
+    got = [list(DistributedSliceSampler(data, num_replicas=4, rank=r)) for r in range(4)]
+    # reference sampler.py:208-219: ceil(10/4)=3 per rank, tail wraps to the head
+    assert got == [[0, 1, 2], [3, 4, 5], [6, 7, 8], [9, 0, 1]]
+    assert [slice_bounds(10, 4, r) for r in range(4)] == [(0, 3, 3), (3, 3, 3), (6, 3, 3), (9, 1, 3)]
+    assert len(DistributedSliceSampler(data, num_replicas=4, rank=3)) == 3
+
+
+def _gloo_worker(rank, world, port, ret):
+    import torch.distributed as dist
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port))
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    try:
+        from openibl_b200.evaluators import sharded_topk
+        from openibl_b200.utils.data.sampler import slice_bounds
+        q, db, gt = synth.make_gallery(n_db=1001, n_q=37, dim=64, sigma=0.5)
+        lo, cnt, per = slice_bounds(db.shape[0], world, rank)
+        shard = torch.zeros(per, db.shape[1])
+        shard[:cnt] = db[lo:lo + cnt]
+
+        def rank_fn(qq, dd, k, idx_base, n_valid):     # oracle stands in for the CUDA kernel
+            d = O.pairwise_distance(qq, dd[:n_valid]).numpy()
+            dk, ik = O.topk_from_distmat(d, min(k, n_valid))
+            pad = k - dk.shape[1]
+            dk = np.pad(dk, ((0, 0), (0, pad)), constant_values=np.inf)
+            ik = np.pad(ik + idx_base, ((0, 0), (0, pad)), constant_values=-1)
+            return torch.from_numpy(dk), torch.from_numpy(ik)
+
+        def merge_fn(cd, ci, k):
+            P, m, kk = cd.shape
+            d = cd.permute(1, 0, 2).reshape(m, P * kk).numpy()
+            i = ci.permute(1, 0, 2).reshape(m, P * kk).numpy()
+            d = np.where(i < 0, np.inf, d)
+            order = np.lexsort((i, d), axis=1)[:, :k]
+            return torch.from_numpy(np.take_along_axis(d, order, 1)), torch.from_numpy(np.take_along_axis(i, order, 1))
+
+        dk, ik = sharded_topk(q, shard, 10, idx_base=lo, n_valid=cnt, _rank_fn=rank_fn, _merge_fn=merge_fn)
+        full = O.pairwise_distance(q, db).numpy()
+        wd, wi = O.topk_from_distmat(full, 10)
+        ret[rank] = bool(np.array_equal(ik.numpy(), wi) and np.allclose(dk.numpy(), wd, atol=1e-6))
+    finally:
+        dist.destroy_process_group()
+
+
+def test_sharded_topk_world2_gloo():
+    """N>1 host logic on CPU: slice the database like DistributedSliceSampler, all-gather the per-shard
+    candidates over gloo, merge; must equal the single-process oracle ranking."""
+    import torch.multiprocessing as mp
+    ctx = mp.get_context("spawn")
+    with ctx.Manager() as mgr:
+        ret = mgr.dict()
+        port = 29600 + os.getpid() % 200
+        procs = [ctx.Process(target=_gloo_worker, args=(r, 2, port, ret)) for r in range(2)]
+        [p.start() for p in procs]
+        [p.join(180) for p in procs]
+        assert all(p.exitcode == 0 for p in procs)
+        assert ret.get(0) is True and ret.get(1) is True
