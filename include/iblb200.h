@@ -65,6 +65,9 @@ int ibl_engine_create(int device, ibl_engine** out);
 int ibl_engine_destroy(ibl_engine* e);
 int ibl_engine_set_conv_mode(ibl_engine* e, int mode);
 int ibl_engine_get_conv_mode(ibl_engine* e, int* mode);
+/* Math mode of the distance and PCA GEMMs (same two values; default tcgen05 bf16x3 with exact fp32
+ * re-scoring of the top-k candidates). */
+int ibl_engine_set_gemm_mode(ibl_engine* e, int mode);
 /* Number of kernels this library has launched through `e` since creation. */
 int ibl_engine_launch_count(ibl_engine* e, uint64_t* count);
 

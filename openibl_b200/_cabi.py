@@ -26,6 +26,7 @@ SIGNATURES = {
     "ibl_engine_create": (c_int, [c_int, POINTER(c_void_p)]),
     "ibl_engine_destroy": (c_int, [_P]),
     "ibl_engine_set_conv_mode": (c_int, [_P, c_int]),
+    "ibl_engine_set_gemm_mode": (c_int, [_P, c_int]),
     "ibl_engine_get_conv_mode": (c_int, [_P, POINTER(c_int)]),
     "ibl_engine_launch_count": (c_int, [_P, POINTER(c_uint64)]),
     "ibl_engine_set_vgg16": (c_int, [_P, POINTER(c_void_p), POINTER(c_void_p), _P]),

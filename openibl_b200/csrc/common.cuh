@@ -79,6 +79,25 @@ int launch_maxpool2x2_planes(const __nv_bfloat16* hi, const __nv_bfloat16* lo, i
                              int C, __nv_bfloat16* yhi, __nv_bfloat16* ylo, cudaStream_t s);
 int tc_selftest(float* max_rel_err, cudaStream_t s);
 
+// tc_gemm.cu  (tcgen05 NT GEMM on bf16 hi/lo planes: distance/top-16, dense distance, PCA partials)
+int dist_top16_max_runs(int m, int n_valid);
+int launch_dist_top16_tc(const __nv_bfloat16* q_hi, const __nv_bfloat16* q_lo, const float* qn, int m,
+                         const __nv_bfloat16* d_hi, const __nv_bfloat16* d_lo, const float* dn, int n,
+                         int n_valid, int K, float* cand_d, long long* cand_i, int max_runs, int* runs_out,
+                         cudaStream_t s);
+int launch_dist_dense_tc(const __nv_bfloat16* q_hi, const __nv_bfloat16* q_lo, const float* qn, int m,
+                         const __nv_bfloat16* d_hi, const __nv_bfloat16* d_lo, const float* dn, int n, int K,
+                         float* out, long long ld_out, cudaStream_t s);
+int pca_tc_splits(int P, int D);
+int launch_pca_partial_tc(const __nv_bfloat16* w_hi, const __nv_bfloat16* w_lo, int P,
+                          const __nv_bfloat16* v_hi, const __nv_bfloat16* v_lo, int N, int D,
+                          float* partial, int* splits_out, cudaStream_t s);
+int launch_rescore_sort(const float* q, const float* qn, int m, const float* db, const float* dbn, int d,
+                        const long long* cand_i, int kc, int k_out, long long idx_base, float* out_dist,
+                        long long* out_idx, cudaStream_t s);
+int launch_pca_finalize(const float* partial, int splits, int N, int P, const float* bias, float* out,
+                        cudaStream_t s);
+
 // netvlad.cu
 struct NetvladWorkspace {
   float* assign = nullptr;   // [N,S,K]  soft-assignment * inv-norm handled in kernel

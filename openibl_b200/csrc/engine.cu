@@ -55,6 +55,7 @@ using namespace ibl;
 struct ibl_engine {
   int device = 0;
   int conv_mode = IBL_CONV_TC_BF16X3;
+  int gemm_mode = IBL_CONV_TC_BF16X3;   // distance / PCA GEMMs: same two math modes
   uint64_t launches = 0;
   bool vgg_ready = false;
   ConvParams conv[13];
@@ -72,6 +73,9 @@ struct ibl_engine {
   DevBuf pca_partial;
   DevBuf qn, dbn, dist_chunk, cand_d, cand_i;
   DevBuf stage_in, stage_out, stage_out2;
+  DevBuf q_pl, db_pl, v_pl, pca_pl;     // bf16 hi|lo planes of queries, database shard, descriptors, PCA W
+  const float* pca_pl_src = nullptr;    // W pointer the cached planes were made from
+  DevBuf mrg_d, mrg_i;
 };
 
 namespace {
@@ -197,7 +201,8 @@ int ibl_engine_destroy(ibl_engine* e) {
   }
   DevBuf* bufs[] = {&e->act[0], &e->act[1], &e->feat, &e->nv_assign, &e->nv_inv, &e->nv_raw, &e->vlad,
                     &e->pca_partial, &e->qn, &e->dbn, &e->dist_chunk, &e->cand_d, &e->cand_i,
-                    &e->stage_in, &e->stage_out, &e->stage_out2};
+                    &e->stage_in, &e->stage_out, &e->stage_out2, &e->q_pl, &e->db_pl, &e->v_pl, &e->pca_pl,
+                    &e->mrg_d, &e->mrg_i};
   for (DevBuf* b : bufs) b->release();
   delete e;
   return IBL_OK;
@@ -212,6 +217,12 @@ int ibl_engine_set_conv_mode(ibl_engine* e, int mode) {
 int ibl_engine_get_conv_mode(ibl_engine* e, int* mode) {
   IBL_REQUIRE(e && mode, "null argument");
   *mode = e->conv_mode;
+  return IBL_OK;
+}
+int ibl_engine_set_gemm_mode(ibl_engine* e, int mode) {
+  IBL_REQUIRE(e, "null engine");
+  IBL_REQUIRE(mode == IBL_CONV_SIMT_FP32 || mode == IBL_CONV_TC_BF16X3, "unknown gemm mode");
+  e->gemm_mode = mode;
   return IBL_OK;
 }
 int ibl_engine_launch_count(ibl_engine* e, uint64_t* count) {
@@ -264,6 +275,15 @@ int ibl_engine_set_pca(ibl_engine* e, const float* W, const float* b, int P, int
   e->pca_b = b;
   e->pca_P = P;
   e->pca_D = D;
+  e->pca_pl_src = nullptr;
+  if (D % 64 == 0) {
+    DeviceGuard g(e->device);
+    const size_t n = (size_t)P * D;
+    IBL_RET(e->pca_pl.ensure(n * 4));
+    IBL_RET(launch_f32_to_planes(W, n, e->pca_pl.as<__nv_bfloat16>(), e->pca_pl.as<__nv_bfloat16>() + n, S(stream)));
+    e->launches++;
+    e->pca_pl_src = W;
+  }
   return IBL_OK;
 }
 
@@ -320,6 +340,24 @@ int ibl_pca_l2(ibl_engine* e, const float* v, int N, int D, const float* W, cons
   IBL_REQUIRE(N >= 1 && P >= 1 && D >= 4, "bad shape");
   IBL_REQUIRE((size_t)P * sizeof(float) <= 48 * 1024, "PCA output dim above 12288 is not supported");
   DeviceGuard g(e->device);
+  if (e->gemm_mode == IBL_CONV_TC_BF16X3 && W == e->pca_pl_src && P == e->pca_P && D == e->pca_D) {
+    const size_t nw = (size_t)P * D;
+    const int splits = pca_tc_splits(P, D);
+    for (int n0 = 0; n0 < N; n0 += 32) {
+      const int nb = N - n0 < 32 ? N - n0 : 32;
+      const size_t nv = (size_t)nb * D;
+      IBL_RET(e->v_pl.ensure(nv * 4));
+      IBL_RET(e->pca_partial.ensure((size_t)splits * nb * P * sizeof(float)));
+      __nv_bfloat16* vh = e->v_pl.as<__nv_bfloat16>();
+      IBL_RET(launch_f32_to_planes(v + (size_t)n0 * D, nv, vh, vh + nv, S(stream)));
+      int sp = 0;
+      IBL_RET(launch_pca_partial_tc(e->pca_pl.as<__nv_bfloat16>(), e->pca_pl.as<__nv_bfloat16>() + nw, P, vh,
+                                    vh + nv, nb, D, e->pca_partial.as<float>(), &sp, S(stream)));
+      IBL_RET(launch_pca_finalize(e->pca_partial.as<float>(), sp, nb, P, b, out + (size_t)n0 * P, S(stream)));
+      e->launches += 3;
+    }
+    return IBL_OK;
+  }
   // enough K-splits to fill the machine: tiles = ceil(P/128)*ceil(N/64)*splits >= ~2 waves of 148 SMs
   int tiles = cdiv(P, 128) * cdiv(N, 64);
   int splits = cdiv(2 * 148, tiles);
@@ -408,6 +446,18 @@ int ibl_l2dist_dense(ibl_engine* e, const float* q, int m, const float* db, int 
   IBL_RET(e->dbn.ensure((size_t)n * sizeof(float)));
   IBL_RET(launch_row_sqnorm(q, m, d, e->qn.as<float>(), S(stream)));
   IBL_RET(launch_row_sqnorm(db, n, d, e->dbn.as<float>(), S(stream)));
+  if (e->gemm_mode == IBL_CONV_TC_BF16X3 && d % 64 == 0) {
+    const size_t qe = (size_t)m * d, de = (size_t)n * d;
+    IBL_RET(e->q_pl.ensure(qe * 4));
+    IBL_RET(e->db_pl.ensure(de * 4));
+    __nv_bfloat16 *qh = e->q_pl.as<__nv_bfloat16>(), *dh = e->db_pl.as<__nv_bfloat16>();
+    IBL_RET(launch_f32_to_planes(q, qe, qh, qh + qe, S(stream)));
+    IBL_RET(launch_f32_to_planes(db, de, dh, dh + de, S(stream)));
+    IBL_RET(launch_dist_dense_tc(qh, qh + qe, e->qn.as<float>(), m, dh, dh + de, e->dbn.as<float>(), n, d, out, n,
+                                 S(stream)));
+    e->launches += 5;
+    return IBL_OK;
+  }
   IBL_RET(launch_l2dist_dense(q, e->qn.as<float>(), m, db, e->dbn.as<float>(), n, d, out, n, S(stream)));
   e->launches += 3;
   return IBL_OK;
@@ -420,6 +470,75 @@ int ibl_l2dist_topk(ibl_engine* e, const float* q, int m, const float* db, int n
   IBL_REQUIRE(n_valid >= 0 && n_valid <= n, "n_valid out of range");
   IBL_REQUIRE(k >= 1 && k <= 128, "top-k supports 1 <= k <= 128");
   DeviceGuard g(e->device);
+  if (e->gemm_mode == IBL_CONV_TC_BF16X3 && d % 64 == 0 && n_valid > 0) {
+    cudaStream_t s = S(stream);
+    IBL_RET(e->qn.ensure((size_t)m * sizeof(float)));
+    IBL_RET(e->dbn.ensure((size_t)n * sizeof(float)));
+    IBL_RET(launch_row_sqnorm(q, m, d, e->qn.as<float>(), s));
+    IBL_RET(launch_row_sqnorm(db, n, d, e->dbn.as<float>(), s));
+    const size_t qe = (size_t)m * d, de = (size_t)n * d;
+    IBL_RET(e->q_pl.ensure(qe * 4));
+    IBL_RET(e->db_pl.ensure(de * 4));
+    __nv_bfloat16 *qh = e->q_pl.as<__nv_bfloat16>(), *dh = e->db_pl.as<__nv_bfloat16>();
+    IBL_RET(launch_f32_to_planes(q, qe, qh, qh + qe, s));
+    IBL_RET(launch_f32_to_planes(db, de, dh, dh + de, s));
+    e->launches += 4;
+    const int kc = 16;                           // candidates kept per query before exact re-scoring
+    if (k <= 12) {
+      const int max_runs = dist_top16_max_runs(m, n_valid);
+      IBL_RET(e->cand_d.ensure((size_t)max_runs * m * kc * sizeof(float)));
+      IBL_RET(e->cand_i.ensure((size_t)max_runs * m * kc * sizeof(int64_t)));
+      int runs = 0;
+      IBL_RET(launch_dist_top16_tc(qh, qh + qe, e->qn.as<float>(), m, dh, dh + de, e->dbn.as<float>(), n,
+                                   n_valid, d, e->cand_d.as<float>(), e->cand_i.as<long long>(), max_runs,
+                                   &runs, s));
+      e->launches++;
+      const long long* ci = e->cand_i.as<long long>();
+      if (runs > 1) {
+        IBL_RET(e->mrg_d.ensure((size_t)m * kc * sizeof(float)));
+        IBL_RET(e->mrg_i.ensure((size_t)m * kc * sizeof(int64_t)));
+        IBL_RET(launch_topk_merge(e->cand_d.as<float>(), e->cand_i.as<int64_t>(), runs, m, kc, kc,
+                                  e->mrg_d.as<float>(), e->mrg_i.as<int64_t>(), s));
+        e->launches++;
+        ci = e->mrg_i.as<long long>();
+      }
+      IBL_RET(launch_rescore_sort(q, e->qn.as<float>(), m, db, e->dbn.as<float>(), d, ci, kc, k, idx_base,
+                                  out_dist, reinterpret_cast<long long*>(out_idx), s));
+      e->launches++;
+      return IBL_OK;
+    }
+    // k > 12: dense tiles on the tensor cores, row select, then the same exact re-scoring
+    const int CHT = 32768;
+    const int ncht = cdiv(n_valid, CHT);
+    const int kk = k + 8 > 128 ? 128 : k + 8;
+    IBL_REQUIRE((long long)ncht * kk <= 8192, "database shard too large for one call; shard it");
+    const int chw = n_valid < CHT ? cdiv(n_valid, 4) * 4 : CHT;
+    IBL_RET(e->dist_chunk.ensure((size_t)m * chw * sizeof(float)));
+    IBL_RET(e->cand_d.ensure((size_t)ncht * m * kk * sizeof(float)));
+    IBL_RET(e->cand_i.ensure((size_t)ncht * m * kk * sizeof(int64_t)));
+    for (int c = 0; c < ncht; ++c) {
+      const int j0 = c * CHT;
+      const int nc = (n_valid - j0 < CHT) ? (n_valid - j0) : CHT;
+      IBL_RET(launch_dist_dense_tc(qh, qh + qe, e->qn.as<float>(), m, dh + (size_t)j0 * d, dh + de + (size_t)j0 * d,
+                                   e->dbn.as<float>() + j0, nc, d, e->dist_chunk.as<float>(), chw, s));
+      IBL_RET(launch_topk_rows(e->dist_chunk.as<float>(), chw, m, nc, kk, j0, e->cand_d.as<float>() + (size_t)c * m * kk,
+                               e->cand_i.as<int64_t>() + (size_t)c * m * kk, false, s));
+      e->launches += 2;
+    }
+    const long long* ci = e->cand_i.as<long long>();
+    if (ncht > 1) {
+      IBL_RET(e->mrg_d.ensure((size_t)m * kk * sizeof(float)));
+      IBL_RET(e->mrg_i.ensure((size_t)m * kk * sizeof(int64_t)));
+      IBL_RET(launch_topk_merge(e->cand_d.as<float>(), e->cand_i.as<int64_t>(), ncht, m, kk, kk,
+                                e->mrg_d.as<float>(), e->mrg_i.as<int64_t>(), s));
+      e->launches++;
+      ci = e->mrg_i.as<long long>();
+    }
+    IBL_RET(launch_rescore_sort(q, e->qn.as<float>(), m, db, e->dbn.as<float>(), d, ci, kk, k, idx_base, out_dist,
+                                reinterpret_cast<long long*>(out_idx), s));
+    e->launches++;
+    return IBL_OK;
+  }
   const int CH = 32768;                         // database rows per dense chunk
   const int nch = n_valid > 0 ? cdiv(n_valid, CH) : 1;
   IBL_REQUIRE((long long)nch * k <= 8192, "database shard too large for one call; shard it");

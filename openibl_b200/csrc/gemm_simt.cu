@@ -144,6 +144,13 @@ pca_finalize_kernel(const float* __restrict__ partial, int splits, int N, int P,
   for (int p = threadIdx.x; p < P; p += blockDim.x) out[n * P + p] = row[p] * inv;
 }
 
+int launch_pca_finalize(const float* partial, int splits, int N, int P, const float* bias, float* out,
+                        cudaStream_t s) {
+  pca_finalize_kernel<<<N, 256, P * sizeof(float), s>>>(partial, splits, N, P, bias, out);
+  IBL_CUDA_OK(cudaGetLastError());
+  return IBL_OK;
+}
+
 int launch_pca_l2(const float* v, int N, int D, const float* W, const float* b, int P,
                   float* partial, int splits, float* out, cudaStream_t s, uint64_t* launches) {
   IBL_REQUIRE(D % 4 == 0, "PCA input dim must be a multiple of 4");

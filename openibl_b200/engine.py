@@ -85,6 +85,9 @@ class Engine:
     def conv_mode(self, mode: int) -> None:
         check(self.lib.ibl_engine_set_conv_mode(self.h, int(mode)), "ibl_engine_set_conv_mode")
 
+    def set_gemm_mode(self, mode: int) -> None:
+        check(self.lib.ibl_engine_set_gemm_mode(self.h, int(mode)), "ibl_engine_set_gemm_mode")
+
     @property
     def launch_count(self) -> int:
         c = c_uint64()
@@ -113,6 +116,10 @@ class Engine:
               "ibl_engine_set_netvlad")
 
     def set_pca(self, weight: torch.Tensor, bias: torch.Tensor) -> None:
+        key = (weight.data_ptr(), weight._version, bias.data_ptr(), bias._version)
+        if key == getattr(self, "_pca_key", None):
+            return
+        self._pca_key = key
         P = weight.shape[0]
         w = _require_cuda(weight.detach().reshape(P, -1), "pca weight")
         b = _require_cuda(bias.detach().reshape(-1), "pca bias")

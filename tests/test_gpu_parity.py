@@ -14,7 +14,12 @@ from openibl_b200 import synth
 pytestmark = pytest.mark.gpu
 
 DESC_TOL = 1e-4        # north-star descriptor tolerance (relative L2, fp32 reference)
-FEAT_TOL_TC = 6e-5     # conv5_3 map through 12 bf16x3 tensor-core layers (measured ~1.2e-5, emulated)
+# conv5_3 map through 12 bf16x3 tensor-core layers.  Measured 7.7e-5..9.4e-5, almost all of it one
+# uniform scale factor (1 - 9e-5): the tcgen05 fp32 accumulator truncates toward zero (bias ~ -2^-26
+# per MMA, tools/diag_tc_error.py), which the L2 normalisations downstream cancel exactly.  With the
+# best-fit scalar removed the residual is the bf16x3 representation error (FEAT_TOL_TC_DESCALED).
+FEAT_TOL_TC = 1.5e-4
+FEAT_TOL_TC_DESCALED = 3e-5
 FEAT_TOL_SIMT = 5e-6   # fp32 CUDA cores: summation-order differences only
 
 
@@ -28,6 +33,14 @@ def eng():
 def O():
     from oracle import ibl_oracle
     return ibl_oracle
+
+
+def descaled_rel_l2(a, b):
+    """rel-L2 after removing the best-fit scalar between a and b."""
+    a = np.asarray(a, dtype=np.float64).ravel()
+    b = np.asarray(b, dtype=np.float64).ravel()
+    s = float(a @ b) / float(a @ a)
+    return float(np.linalg.norm(a * s - b) / np.linalg.norm(b))
 
 
 def _modes():
@@ -97,6 +110,7 @@ def test_small_96x128_every_stage_vs_reference(eng):
         eng.conv_mode = mode
         nhwc, nchw, pool = eng.vgg16_forward(x, want_nchw=True, want_pool=True, want_nhwc=True)
         assert rel_l2(nchw.cpu(), g["feat"]) < ftol, name
+        assert descaled_rel_l2(nchw.cpu(), g["feat"]) < min(ftol, FEAT_TOL_TC_DESCALED), name
         assert rel_l2(nhwc.permute(0, 3, 1, 2).cpu(), g["feat"]) < ftol, name
         assert rel_l2(pool.cpu(), g["pool"]) < ftol * 2, name
         raw, nrm = eng.netvlad_forward(nchw, sdd["net_vlad.conv.weight"], sdd["net_vlad.centroids"],
@@ -134,7 +148,8 @@ def test_hub_480x640_config_vs_reference(eng):
         eng.conv_mode = mode
         _, nchw, pool = eng.vgg16_forward(x)
         assert rel_l2(nchw[:, ::8, ::3, ::4].cpu(), g["feat_sub"]) < ftol, name
-        assert abs(nchw.double().abs().sum().item() - g["feat_abs_sum"]) < 1e-5 * g["feat_abs_sum"]
+        assert descaled_rel_l2(nchw[:, ::8, ::3, ::4].cpu(), g["feat_sub"]) < min(ftol, FEAT_TOL_TC_DESCALED), name
+        assert abs(nchw.double().abs().sum().item() - g["feat_abs_sum"]) < 2 * ftol * g["feat_abs_sum"]
         assert rel_l2(pool.cpu(), g["pool"]) < 2 * ftol, name
         vlad, _ = eng.extract(x, pca=False)
         assert rel_l2(vlad.cpu(), g["vlad"]) < DESC_TOL / 4, name
@@ -204,27 +219,47 @@ def test_netvlad_ragged_sizes_vs_oracle(eng, O):
 # ---------------------------------------------------------------------------------------------
 # stage (iii-a): PCA-whiten + L2
 # ---------------------------------------------------------------------------------------------
+GEMM_MODES = [("simt", 0, 1e-5), ("tc", 1, 3e-5)]   # (name, ibl gemm mode, rel-L2 tolerance)
+
+
+@pytest.fixture(autouse=True)
+def _default_modes(eng):
+    yield
+    eng.set_gemm_mode(1)
+    eng.conv_mode = 1
+
+
 def test_pca_unit_vs_reference(eng):
     g = load_golden("pca_unit")
     p = synth.make_pca_params(seed=9, in_dim=32768, out_dim=64)
     gen = torch.Generator().manual_seed(12)
     v = torch.nn.functional.normalize(torch.randn(5, 32768, generator=gen), dim=1)
-    out = eng.pca_l2(v.cuda(), p["weight"].cuda(), p["bias"].cuda())
-    assert rel_l2(out.cpu(), g["out"]) < 1e-5
+    w, b = p["weight"].cuda(), p["bias"].cuda()
+    for name, mode, tol in GEMM_MODES:
+        eng.set_gemm_mode(mode)
+        eng._pca_key = None
+        eng.set_pca(w, b)                       # registers (and, for tcgen05, re-lays-out) W
+        out = eng.pca_l2(v.cuda(), w, b)
+        assert rel_l2(out.cpu(), g["out"]) < tol, name
 
 
 def test_pca_full_size_vs_oracle(eng, O):
     p = synth.make_pca_params(seed=1, in_dim=32768, out_dim=4096)
     gen = torch.Generator().manual_seed(13)
+    w, b = p["weight"].cuda(), p["bias"].cuda()
+    eng._pca_key = None
+    eng.set_pca(w, b)
     for n in (1, 33):
         v = torch.nn.functional.normalize(torch.randn(n, 32768, generator=gen), dim=1)
         want = O.pca_whiten(v, p["weight"], p["bias"])
-        got = eng.pca_l2(v.cuda(), p["weight"].cuda(), p["bias"].cuda())
-        assert rel_l2(got.cpu(), want) < 1e-5
+        for name, mode, tol in GEMM_MODES:
+            eng.set_gemm_mode(mode)
+            got = eng.pca_l2(v.cuda(), w, b)
+            assert rel_l2(got.cpu(), want) < tol, (name, n)
     from openibl_b200.pca import PCA
     pca = PCA(4096)
-    pca.weight, pca.bias = p["weight"].cuda(), p["bias"].cuda()
-    assert rel_l2(pca.infer(v.cuda()).cpu(), want) < 1e-5
+    pca.weight, pca.bias = w, b
+    assert rel_l2(pca.infer(v.cuda()).cpu(), want) < 3e-5
 
 
 # ---------------------------------------------------------------------------------------------
@@ -234,11 +269,14 @@ def test_retrieval_vs_reference_golden(eng):
     from openibl_b200.evaluators import evaluate_all, pairwise_distance, recalls_from_topk
     g = load_golden("retrieval")
     q, db, gt = synth.make_gallery(n_db=1500, n_q=300, dim=512, sigma=0.28)
-    d = eng.l2dist_dense(q.cuda(), db.cuda())
-    assert np.abs(d[:32].cpu().numpy() - g["dist_sub"]).max() < 2e-5
-    dk, ik = eng.l2dist_topk(q.cuda(), db.cuda(), 10)
-    assert np.array_equal(ik.cpu().numpy(), g["top10"])
-    assert np.abs(dk.cpu().numpy() - g["top10_dist"]).max() < 2e-5
+    for name, mode, _ in GEMM_MODES:
+        eng.set_gemm_mode(mode)
+        d = eng.l2dist_dense(q.cuda(), db.cuda())
+        # dense matrix: fp32 CUDA cores 2e-5 abs; tcgen05 bf16x3 (no re-scoring on this path) 1e-4 abs
+        assert np.abs(d[:32].cpu().numpy() - g["dist_sub"]).max() < (2e-5 if mode == 0 else 1e-4), name
+        dk, ik = eng.l2dist_topk(q.cuda(), db.cuda(), 10)     # top-k is re-scored in exact fp32
+        assert np.array_equal(ik.cpu().numpy(), g["top10"]), name
+        assert np.abs(dk.cpu().numpy() - g["top10_dist"]).max() < 2e-5, name
     gallery = [("d%05d" % i, i // 3, 0.0, 0.0) for i in range(1500)]
     query = [("q%05d" % i, i, 0.0, 0.0) for i in range(300)]
     gt_list = [np.array([int(t)]) for t in gt]
@@ -260,11 +298,17 @@ def test_topk_edge_cases(eng, O):
     q, db, _ = synth.make_gallery(n_db=700, n_q=9, dim=64, sigma=0.5)
     qd, dbd = q.cuda(), db.cuda()
     d = O.pairwise_distance(q, db).numpy()
-    # k = 1, k = 128, padded shard (n_valid < n), idx_base, duplicates (ties -> lowest index)
-    for k in (1, 128):
+    for name, mode, _ in GEMM_MODES:
+        eng.set_gemm_mode(mode)
+        _topk_edge_cases(eng, O, q, db, qd, dbd, d)
+
+
+def _topk_edge_cases(eng, O, q, db, qd, dbd, d):
+    # k = 1, k = 12/13 (register top-16 vs dense path), k = 128, padded shard, idx_base, duplicates
+    for k in (1, 12, 13, 128):
         dk, ik = eng.l2dist_topk(qd, dbd, k)
         wd, wi = O.topk_from_distmat(d, k)
-        assert np.array_equal(ik.cpu().numpy(), wi) and np.allclose(dk.cpu().numpy(), wd, atol=1e-5)
+        assert np.array_equal(ik.cpu().numpy(), wi) and np.allclose(dk.cpu().numpy(), wd, atol=1e-5), k
     dk, ik = eng.l2dist_topk(qd, dbd, 10, idx_base=5000, n_valid=333)
     wd, wi = O.topk_from_distmat(d[:, :333], 10)
     assert np.array_equal(ik.cpu().numpy(), wi + 5000)
@@ -286,7 +330,14 @@ def test_retrieval_pitts30k_shape_properties(eng):
     """configs[2] size: 6.8k x 10k x 4096.  Size-independent properties + a subset against torch fp64."""
     q, db, gt = synth.make_gallery(10000, 6800, 4096)
     qd, dbd = q.cuda(), db.cuda()
-    dk, ik = eng.l2dist_topk(qd, dbd, 10)
+    eng.set_gemm_mode(0)
+    dk0, ik0 = eng.l2dist_topk(qd, dbd, 10)                           # fp32 CUDA cores
+    eng.set_gemm_mode(1)
+    dk, ik = eng.l2dist_topk(qd, dbd, 10)                             # tcgen05 + exact re-scoring
+    assert float((ik == ik0).float().mean()) > 0.999
+    assert float((dk - dk0).abs().max()) < 5e-6
+    dk120, ik120 = eng.l2dist_topk(qd[:512].contiguous(), dbd, 120)    # dense-tile path (Tokyo nms, k=120)
+    assert bool((ik120[:, :10] == ik[:512]).float().mean() > 0.999)
     assert bool((dk[:, 1:] >= dk[:, :-1]).all())                       # sorted ascending
     assert int(ik.min()) >= 0 and int(ik.max()) < 10000
     assert bool((ik.sort(dim=1).values[:, 1:] != ik.sort(dim=1).values[:, :-1]).all())   # no duplicates
