@@ -106,6 +106,8 @@ class Engine:
         ba = (c_void_p * 13)(*[b.data_ptr() for b in bs])
         check(self.lib.ibl_engine_set_vgg16(self.h, wa, ba, _stream(self.device)), "ibl_engine_set_vgg16")
         self._vgg_key = key
+        # keep the tensors alive: the key is (address, version), so the addresses must not be recycled
+        self._keep["vgg"] = (list(weights), list(biases), ws, bs)
 
     def set_netvlad(self, conv_w: torch.Tensor, centroids: torch.Tensor) -> None:
         K, C = centroids.shape

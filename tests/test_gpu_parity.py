@@ -19,7 +19,7 @@ DESC_TOL = 1e-4        # north-star descriptor tolerance (relative L2, fp32 refe
 # per MMA, tools/diag_tc_error.py), which the L2 normalisations downstream cancel exactly.  With the
 # best-fit scalar removed the residual is the bf16x3 representation error (FEAT_TOL_TC_DESCALED).
 FEAT_TOL_TC = 1.5e-4
-FEAT_TOL_TC_DESCALED = 3e-5
+FEAT_TOL_TC_DESCALED = 5e-5
 FEAT_TOL_SIMT = 5e-6   # fp32 CUDA cores: summation-order differences only
 
 
