@@ -165,6 +165,15 @@ int ibl_debug_conv3x3(ibl_engine* e, const float* x_nhwc, int N, int H, int W, i
                       const float* w_oihw, const float* bias, int cout, int relu, int pool, int mode,
                       int bn_override, float* y_nhwc, void* stream);
 
+/* MN-major tcgen05 operand self-test: C[128,64] = A^T B for A [128 k,128 m], B [128 k,64 n] (fp32, device),
+ * bf16x3 on the tensor core.  Synchronises. */
+int ibl_debug_gemm_tn(ibl_engine* e, const float* A, const float* B, float* C, void* stream);
+/* Average device time (ms) of one backbone layer over `reps` launches, weights from the engine
+ * (tools/bench_layers.py).  layer 0 = conv1_1 (x NCHW [N,3,H,W]); 1..12 = conv1_2..conv5_3
+ * (x NHWC [N,H,W,Cin] fp32).  Synchronises. */
+int ibl_debug_time_layer(ibl_engine* e, int layer, const float* x, int N, int H, int W, int bn_override,
+                         int reps, float* ms_out);
+
 #ifdef __cplusplus
 }
 #endif

@@ -74,10 +74,20 @@ struct TcConvPlan;   // opaque per-engine cache of TMA descriptors
 int tc_driver_init();   // resolves cuTensorMapEncodeTiled; IBL_ERR_NO_DEVICE if unavailable
 int launch_conv3x3_tc(const __nv_bfloat16* x_hi, const __nv_bfloat16* x_lo, const ConvParams& p,
                       int N, int H, int W, int cin, int cout, bool relu, bool pool,
-                      __nv_bfloat16* y_hi, __nv_bfloat16* y_lo, float* y_f32, cudaStream_t s);
+                      __nv_bfloat16* y_hi, __nv_bfloat16* y_lo, float* y_f32, cudaStream_t s,
+                      float* ssq = nullptr, int* ssq_parts = nullptr);
 int launch_maxpool2x2_planes(const __nv_bfloat16* hi, const __nv_bfloat16* lo, int N, int H, int W,
                              int C, __nv_bfloat16* yhi, __nv_bfloat16* ylo, cudaStream_t s);
 int tc_selftest(float* max_rel_err, cudaStream_t s);
+// tc_netvlad.cu
+int debug_gemm_tn(const float* A, const float* B, float* C, cudaStream_t s);
+int netvlad_tc_units(int B, int S);
+int launch_netvlad_tc(const __nv_bfloat16* x_hi, const __nv_bfloat16* x_lo, int B, int S,
+                      const __nv_bfloat16* w_hi, const __nv_bfloat16* w_lo, const float* ssq, int ssq_parts,
+                      const float* cent, bool normalize_input, float* part, float* asum_part,
+                      float* vlad_raw, float* vlad_norm, cudaStream_t s);
+int launch_global_maxpool_planes(const __nv_bfloat16* hi, const __nv_bfloat16* lo, int N, int S, int C, float* y,
+                                 cudaStream_t s);
 
 // tc_gemm.cu  (tcgen05 NT GEMM on bf16 hi/lo planes: distance/top-16, dense distance, PCA partials)
 int dist_top16_max_runs(int m, int n_valid);

@@ -76,6 +76,15 @@ struct ibl_engine {
   DevBuf q_pl, db_pl, v_pl, pca_pl;     // bf16 hi|lo planes of queries, database shard, descriptors, PCA W
   const float* pca_pl_src = nullptr;    // W pointer the cached planes were made from
   DevBuf mrg_d, mrg_i;
+  DevBuf ssq, nv_part, nv_asum, nvw_pl;  // fused NetVLAD: |x|^2 partials, unit partials, W planes [64,512]
+  const float* nvw_pl_src = nullptr;
+};
+
+// conv5_3 output as bf16 hi/lo planes (fused-NetVLAD path)
+struct FeatPlanes {
+  __nv_bfloat16* hi = nullptr;
+  __nv_bfloat16* lo = nullptr;
+  int ssq_parts = 0;
 };
 
 namespace {
@@ -95,7 +104,7 @@ struct DeviceGuard {
 };
 
 int vgg_forward_impl(ibl_engine* e, const float* x, int N, int H, int W, float* feat_nhwc,
-                     cudaStream_t s) {
+                     cudaStream_t s, FeatPlanes* planes_out = nullptr) {
   // largest activation: conv1_x output, N*H*W*64 values of 4 bytes (fp32, or bf16 hi + bf16 lo)
   const size_t act_bytes = (size_t)N * H * W * 64 * 4;
   IBL_RET(e->act[0].ensure(act_bytes));
@@ -134,6 +143,17 @@ int vgg_forward_impl(ibl_engine* e, const float* x, int N, int H, int W, float* 
     const size_t in_elems = (size_t)N * h * w * L.cin;
     const int oh = L.pool ? h / 2 : h, ow = L.pool ? w / 2 : w;
     const size_t out_elems = (size_t)N * oh * ow * L.cout;
+    if (last && planes_out) {
+      // fused-NetVLAD path: conv5_3 leaves hi/lo planes + per-pixel |x|^2 partials instead of fp32
+      IBL_RET(e->ssq.ensure((size_t)8 * N * oh * ow * sizeof(float)));
+      IBL_RET(launch_conv3x3_tc(hi_of(cur, in_elems), lo_of(cur, in_elems), e->conv[l], N, h, w, L.cin,
+                                L.cout, L.relu, L.pool, hi_of(cur ^ 1, out_elems), lo_of(cur ^ 1, out_elems),
+                                nullptr, s, e->ssq.as<float>(), &planes_out->ssq_parts));
+      planes_out->hi = hi_of(cur ^ 1, out_elems);
+      planes_out->lo = lo_of(cur ^ 1, out_elems);
+      e->launches++;
+      return IBL_OK;
+    }
     IBL_RET(launch_conv3x3_tc(hi_of(cur, in_elems), lo_of(cur, in_elems), e->conv[l], N, h, w, L.cin,
                               L.cout, L.relu, L.pool, last ? nullptr : hi_of(cur ^ 1, out_elems),
                               last ? nullptr : lo_of(cur ^ 1, out_elems), last ? feat_nhwc : nullptr, s));
@@ -202,7 +222,7 @@ int ibl_engine_destroy(ibl_engine* e) {
   DevBuf* bufs[] = {&e->act[0], &e->act[1], &e->feat, &e->nv_assign, &e->nv_inv, &e->nv_raw, &e->vlad,
                     &e->pca_partial, &e->qn, &e->dbn, &e->dist_chunk, &e->cand_d, &e->cand_i,
                     &e->stage_in, &e->stage_out, &e->stage_out2, &e->q_pl, &e->db_pl, &e->v_pl, &e->pca_pl,
-                    &e->mrg_d, &e->mrg_i};
+                    &e->mrg_d, &e->mrg_i, &e->ssq, &e->nv_part, &e->nv_asum, &e->nvw_pl};
   for (DevBuf* b : bufs) b->release();
   delete e;
   return IBL_OK;
@@ -256,7 +276,6 @@ int ibl_engine_set_vgg16(ibl_engine* e, const float* const* w13, const float* co
 
 int ibl_engine_set_netvlad(ibl_engine* e, const float* conv_w, const float* centroids, int K, int C,
                            void* stream) {
-  (void)stream;
   IBL_REQUIRE(e && conv_w && centroids, "null argument");
   IBL_REQUIRE(K == 64, "NetVLAD kernels are built for K=64 clusters");
   IBL_REQUIRE(C >= 4 && C % 4 == 0, "NetVLAD dim must be a positive multiple of 4");
@@ -264,6 +283,15 @@ int ibl_engine_set_netvlad(ibl_engine* e, const float* conv_w, const float* cent
   e->nv_c = centroids;
   e->nv_K = K;
   e->nv_C = C;
+  e->nvw_pl_src = nullptr;
+  if (K == 64 && C == 512) {
+    DeviceGuard g(e->device);
+    const size_t n = (size_t)K * C;
+    IBL_RET(e->nvw_pl.ensure(n * 4));
+    IBL_RET(launch_f32_to_planes(conv_w, n, e->nvw_pl.as<__nv_bfloat16>(), e->nvw_pl.as<__nv_bfloat16>() + n, S(stream)));
+    e->launches++;
+    e->nvw_pl_src = conv_w;
+  }
   return IBL_OK;
 }
 
@@ -314,6 +342,25 @@ int ibl_netvlad_forward(ibl_engine* e, const float* feat, int nhwc, int N, int C
   IBL_REQUIRE(K == 64, "NetVLAD kernels are built for K=64 clusters");
   IBL_REQUIRE(vlad_raw || vlad_norm, "no output requested");
   DeviceGuard g(e->device);
+  if (nhwc && C == 512 && K == 64 && e->gemm_mode == IBL_CONV_TC_BF16X3) {
+    cudaStream_t s = S(stream);
+    const size_t ne = (size_t)N * S_ * C, nw = (size_t)K * C;
+    IBL_RET(e->v_pl.ensure(ne * 4));
+    IBL_RET(e->q_pl.ensure(nw * 4));
+    IBL_RET(e->ssq.ensure((size_t)N * S_ * sizeof(float)));
+    __nv_bfloat16 *xh = e->v_pl.as<__nv_bfloat16>(), *wh = e->q_pl.as<__nv_bfloat16>();
+    IBL_RET(launch_f32_to_planes(feat, ne, xh, xh + ne, s));
+    IBL_RET(launch_f32_to_planes(conv_w, nw, wh, wh + nw, s));
+    IBL_RET(launch_row_sqnorm(feat, N * S_, C, e->ssq.as<float>(), s));
+    const int G = netvlad_tc_units(N, S_);
+    IBL_RET(e->nv_part.ensure((size_t)N * G * 64 * 512 * sizeof(float)));
+    IBL_RET(e->nv_asum.ensure((size_t)N * G * 64 * sizeof(float)));
+    IBL_RET(launch_netvlad_tc(xh, xh + ne, N, S_, wh, wh + nw, e->ssq.as<float>(), 1, centroids,
+                              normalize_input != 0, e->nv_part.as<float>(), e->nv_asum.as<float>(), vlad_raw,
+                              vlad_norm, s));
+    e->launches += 5;
+    return IBL_OK;
+  }
   IBL_RET(e->nv_assign.ensure((size_t)N * S_ * K * sizeof(float)));
   IBL_RET(e->nv_inv.ensure((size_t)N * S_ * sizeof(float)));
   float* raw = vlad_raw;
@@ -396,18 +443,38 @@ int ibl_extract(ibl_engine* e, const float* x, int N, int H, int W, unsigned fla
   for (int n0 = 0; n0 < N; n0 += MB) {
     const int nb = (N - n0 < MB) ? (N - n0) : MB;
     const float* xb = x + (size_t)n0 * 3 * H * W;
-    IBL_RET(e->feat.ensure((size_t)nb * Sp * 512 * sizeof(float)));
-    IBL_RET(vgg_forward_impl(e, xb, nb, H, W, e->feat.as<float>(), S(stream)));
-    if (flags & IBL_OUT_POOL) {
-      IBL_RET(launch_global_maxpool_nhwc(e->feat.as<float>(), nb, Sp, 512, pool + (size_t)n0 * 512, S(stream)));
-      e->launches++;
-    }
     float* vdst = out + (size_t)n0 * out_dim;
     if (pca) {
       IBL_RET(e->vlad.ensure((size_t)nb * D * sizeof(float)));
       vdst = e->vlad.as<float>();
     }
-    IBL_RET(ibl_netvlad_forward(e, e->feat.as<float>(), 1, nb, C, Sp, e->nv_w, e->nv_c, K, 1, nullptr, vdst, stream));
+    const bool fused = e->conv_mode == IBL_CONV_TC_BF16X3 && e->gemm_mode == IBL_CONV_TC_BF16X3 &&
+                       e->nvw_pl_src == e->nv_w && K == 64 && C == 512;
+    if (fused) {
+      // conv5_3 -> hi/lo planes + |x|^2 partials -> one tcgen05 NetVLAD kernel (+ finalize)
+      FeatPlanes fp;
+      IBL_RET(vgg_forward_impl(e, xb, nb, H, W, nullptr, S(stream), &fp));
+      if (flags & IBL_OUT_POOL) {
+        IBL_RET(launch_global_maxpool_planes(fp.hi, fp.lo, nb, Sp, 512, pool + (size_t)n0 * 512, S(stream)));
+        e->launches++;
+      }
+      const int G = netvlad_tc_units(nb, Sp);
+      IBL_RET(e->nv_part.ensure((size_t)nb * G * 64 * 512 * sizeof(float)));
+      IBL_RET(e->nv_asum.ensure((size_t)nb * G * 64 * sizeof(float)));
+      const size_t nw = (size_t)64 * 512;
+      IBL_RET(launch_netvlad_tc(fp.hi, fp.lo, nb, Sp, e->nvw_pl.as<__nv_bfloat16>(), e->nvw_pl.as<__nv_bfloat16>() + nw,
+                                e->ssq.as<float>(), fp.ssq_parts, e->nv_c, true, e->nv_part.as<float>(),
+                                e->nv_asum.as<float>(), nullptr, vdst, S(stream)));
+      e->launches += 2;
+    } else {
+      IBL_RET(e->feat.ensure((size_t)nb * Sp * 512 * sizeof(float)));
+      IBL_RET(vgg_forward_impl(e, xb, nb, H, W, e->feat.as<float>(), S(stream)));
+      if (flags & IBL_OUT_POOL) {
+        IBL_RET(launch_global_maxpool_nhwc(e->feat.as<float>(), nb, Sp, 512, pool + (size_t)n0 * 512, S(stream)));
+        e->launches++;
+      }
+      IBL_RET(ibl_netvlad_forward(e, e->feat.as<float>(), 1, nb, C, Sp, e->nv_w, e->nv_c, K, 1, nullptr, vdst, stream));
+    }
     if (pca)
       IBL_RET(ibl_pca_l2(e, vdst, nb, D, e->pca_W, e->pca_b, e->pca_P, out + (size_t)n0 * out_dim, stream));
   }
@@ -676,6 +743,57 @@ int ibl_debug_conv3x3(ibl_engine* e, const float* x_nhwc, int N, int H, int W, i
     return IBL_ERR_CUDA;
   }
   e->launches += 3;
+  return rc;
+}
+
+int ibl_debug_gemm_tn(ibl_engine* e, const float* A, const float* B, float* C, void* stream) {
+  IBL_REQUIRE(e && A && B && C, "null argument");
+  DeviceGuard g(e->device);
+  e->launches += 3;
+  return debug_gemm_tn(A, B, C, S(stream));
+}
+
+// Timing hooks (tools/bench_layers.py): average device time of one backbone layer over `reps`
+// back-to-back launches, weights taken from the engine (ibl_engine_set_vgg16).  layer 0 = conv1_1
+// (x is NCHW [N,3,H,W]); layers 1..12 take x NHWC [N,H,W,Cin] fp32 (converted to planes once).
+int ibl_debug_time_layer(ibl_engine* e, int layer, const float* x, int N, int H, int W, int bn_override,
+                         int reps, float* ms_out) {
+  IBL_REQUIRE(e && x && ms_out && layer >= 0 && layer < 13 && reps >= 1, "bad argument");
+  if (!e->vgg_ready) { set_last_error("ibl_engine_set_vgg16 was not called"); return IBL_ERR_NOT_READY; }
+  DeviceGuard g(e->device);
+  const ConvLayer& L = kVgg16[layer];
+  const size_t in_e = (size_t)N * H * W * L.cin;
+  const int oh = L.pool ? H / 2 : H, ow = L.pool ? W / 2 : W;
+  const size_t out_e = (size_t)N * oh * ow * L.cout;
+  IBL_RET(e->act[0].ensure((in_e > out_e ? in_e : out_e) * 4));
+  IBL_RET(e->act[1].ensure((in_e > out_e ? in_e : out_e) * 4));
+  cudaEvent_t e0, e1;
+  IBL_CUDA_OK(cudaEventCreate(&e0));
+  IBL_CUDA_OK(cudaEventCreate(&e1));
+  __nv_bfloat16* ih = e->act[0].as<__nv_bfloat16>();
+  __nv_bfloat16* oh_ = e->act[1].as<__nv_bfloat16>();
+  int rc = IBL_OK;
+  if (layer > 0) rc = launch_f32_to_planes(x, in_e, ih, ih + in_e, nullptr);
+  tc_set_bn_override(bn_override);
+  for (int r = -1; r < reps && rc == IBL_OK; ++r) {       // r = -1 is a warm-up launch
+    if (r == 0) cudaEventRecord(e0, nullptr);
+    if (layer == 0)
+      rc = launch_conv1_1(x, e->conv[0], N, H, W, true, nullptr, oh_, oh_ + out_e, nullptr);
+    else
+      rc = launch_conv3x3_tc(ih, ih + in_e, e->conv[layer], N, H, W, L.cin, L.cout, L.relu, L.pool,
+                             layer == 12 ? nullptr : oh_, layer == 12 ? nullptr : oh_ + out_e,
+                             layer == 12 ? e->act[1].as<float>() : nullptr, nullptr);
+  }
+  tc_set_bn_override(0);
+  cudaEventRecord(e1, nullptr);
+  cudaError_t ce = cudaEventSynchronize(e1);
+  float ms = 0.f;
+  cudaEventElapsedTime(&ms, e0, e1);
+  cudaEventDestroy(e0);
+  cudaEventDestroy(e1);
+  if (rc == IBL_OK && ce != cudaSuccess) { set_last_error(cudaGetErrorString(ce)); return IBL_ERR_CUDA; }
+  *ms_out = ms / reps;
+  e->launches += reps + 1;
   return rc;
 }
 

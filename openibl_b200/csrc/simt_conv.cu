@@ -143,9 +143,11 @@ int launch_conv3x3_simt(const float* x, const ConvParams& p, int N, int H, int W
 }
 
 // ------------------------------------------------------------------------------------------
-// conv1_1: NCHW fp32 [N,3,H,W] -> NHWC [N,H,W,64], + bias + ReLU.  One pixel per thread,
-// 128 consecutive pixels per block, outputs staged in shared memory so that the block
-// writes one contiguous 128x64 chunk.  Output either fp32 or bf16 hi/lo planes.
+// conv1_1: NCHW fp32 [N,3,H,W] -> NHWC [N,H,W,64], + bias + ReLU (vgg.py slot 0).  K = 27 does not
+// tile onto tcgen05, so this runs on the CUDA cores: one pixel per thread, 64 accumulators in
+// registers, the 27x64 weights broadcast from shared memory (LDS.128 feeds 4 FMAs).  Each thread
+// writes its pixel's 64 channels as contiguous 16-byte stores (256 B fp32, or 128 B + 128 B of bf16
+// hi/lo planes), so every 128-byte line is fully written by one thread.
 // ------------------------------------------------------------------------------------------
 template <bool PLANES>
 __global__ void __launch_bounds__(128)
@@ -153,59 +155,65 @@ conv1_1_kernel(const float* __restrict__ x, const float* __restrict__ w /*[27][6
                const float* __restrict__ bias, float* __restrict__ y,
                __nv_bfloat16* __restrict__ y_hi, __nv_bfloat16* __restrict__ y_lo, int N, int H,
                int W) {
-  __shared__ float ws[27][64];
-  __shared__ float bs[64];
-  __shared__ float tile[128][65];
+  __shared__ __align__(16) float ws[27][64];
+  __shared__ __align__(16) float bs[64];
   const int t = threadIdx.x;
-  for (int i = t; i < 27 * 64; i += 128) {
-    // w_tck layout is [tap][cin][cout]; k index here = tap*3 + cin
-    ws[i / 64][i % 64] = w[i];
-  }
+  for (int i = t; i < 27 * 64; i += 128) ws[i / 64][i % 64] = w[i];   // w_tck: [tap][cin][cout]
   if (t < 64) bs[t] = bias[t];
   __syncthreads();
   const long long M = (long long)N * H * W;
-  const long long m0 = (long long)blockIdx.x * 128;
-  const long long pm = m0 + t;
+  const long long pm = (long long)blockIdx.x * 128 + t;
+  if (pm >= M) return;
+  const long long pn = pm / ((long long)H * W);
+  const int rem = (int)(pm - pn * (long long)H * W);
+  const int ph = rem / W, pw = rem - (rem / W) * W;
   float acc[64];
 #pragma unroll
   for (int j = 0; j < 64; ++j) acc[j] = bs[j];
-  if (pm < M) {
-    const long long pn = pm / ((long long)H * W);
-    const int rem = (int)(pm - pn * (long long)H * W);
-    const int ph = rem / W, pw = rem - (rem / W) * W;
+  float v[27];
 #pragma unroll
-    for (int tap = 0; tap < 9; ++tap) {
-      const int ih = ph + tap / 3 - 1, iw = pw + tap % 3 - 1;
-      const bool inb = ih >= 0 && ih < H && iw >= 0 && iw < W;
+  for (int tap = 0; tap < 9; ++tap) {
+    const int ih = ph + tap / 3 - 1, iw = pw + tap % 3 - 1;
+    const bool inb = ih >= 0 && ih < H && iw >= 0 && iw < W;
 #pragma unroll
-      for (int c = 0; c < 3; ++c) {
-        float v = 0.f;
-        if (inb) v = __ldg(x + ((pn * 3 + c) * H + ih) * (long long)W + iw);
-        const float* wr = ws[tap * 3 + c];
+    for (int c = 0; c < 3; ++c)
+      v[tap * 3 + c] = inb ? __ldg(x + ((pn * 3 + c) * H + ih) * (long long)W + iw) : 0.f;
+  }
 #pragma unroll
-        for (int j = 0; j < 64; ++j) acc[j] = fmaf(v, wr[j], acc[j]);
-      }
+  for (int k = 0; k < 27; ++k) {
+    const float4* wr = reinterpret_cast<const float4*>(ws[k]);
+#pragma unroll
+    for (int j = 0; j < 16; ++j) {
+      const float4 wv = wr[j];
+      acc[4 * j + 0] = fmaf(v[k], wv.x, acc[4 * j + 0]);
+      acc[4 * j + 1] = fmaf(v[k], wv.y, acc[4 * j + 1]);
+      acc[4 * j + 2] = fmaf(v[k], wv.z, acc[4 * j + 2]);
+      acc[4 * j + 3] = fmaf(v[k], wv.w, acc[4 * j + 3]);
     }
   }
 #pragma unroll
-  for (int j = 0; j < 64; ++j) tile[t][j] = fmaxf(acc[j], 0.f);
-  __syncthreads();
-  long long valid = M - m0;
-  if (valid > 128) valid = 128;
+  for (int j = 0; j < 64; ++j) acc[j] = fmaxf(acc[j], 0.f);
   if (!PLANES) {
-    float* out = y + m0 * 64;
-    for (int e = t; e < (int)valid * 64; e += 128) out[e] = tile[e >> 6][e & 63];
+    float4* o = reinterpret_cast<float4*>(y + pm * 64);
+#pragma unroll
+    for (int j = 0; j < 16; ++j) o[j] = make_float4(acc[4 * j], acc[4 * j + 1], acc[4 * j + 2], acc[4 * j + 3]);
   } else {
-    __nv_bfloat162* oh = reinterpret_cast<__nv_bfloat162*>(y_hi + m0 * 64);
-    __nv_bfloat162* ol = reinterpret_cast<__nv_bfloat162*>(y_lo + m0 * 64);
-    for (int e = t; e < (int)valid * 32; e += 128) {
-      const int p = e >> 5, c = (e & 31) * 2;
-      const float v0 = tile[p][c], v1 = tile[p][c + 1];
-      const __nv_bfloat16 h0 = __float2bfloat16_rn(v0), h1 = __float2bfloat16_rn(v1);
-      const __nv_bfloat16 l0 = __float2bfloat16_rn(v0 - __bfloat162float(h0));
-      const __nv_bfloat16 l1 = __float2bfloat16_rn(v1 - __bfloat162float(h1));
-      oh[e] = __nv_bfloat162(h0, h1);
-      ol[e] = __nv_bfloat162(l0, l1);
+    uint4* oh = reinterpret_cast<uint4*>(y_hi + pm * 64);
+    uint4* ol = reinterpret_cast<uint4*>(y_lo + pm * 64);
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {
+      uint32_t hi[4], lo[4];
+#pragma unroll
+      for (int q = 0; q < 4; ++q) {
+        const float x0 = acc[8 * j + 2 * q], x1 = acc[8 * j + 2 * q + 1];
+        const __nv_bfloat16 h0 = __float2bfloat16_rn(x0), h1 = __float2bfloat16_rn(x1);
+        __nv_bfloat162 hh(h0, h1);
+        __nv_bfloat162 ll = __floats2bfloat162_rn(x0 - __bfloat162float(h0), x1 - __bfloat162float(h1));
+        hi[q] = *reinterpret_cast<uint32_t*>(&hh);
+        lo[q] = *reinterpret_cast<uint32_t*>(&ll);
+      }
+      oh[j] = make_uint4(hi[0], hi[1], hi[2], hi[3]);
+      ol[j] = make_uint4(lo[0], lo[1], lo[2], lo[3]);
     }
   }
 }
@@ -302,6 +310,28 @@ __global__ void global_maxpool_kernel(const float* __restrict__ x, float* __rest
 int launch_global_maxpool_nhwc(const float* x, int N, int S, int C, float* y, cudaStream_t s) {
   dim3 grid((unsigned)cdiv(C, 128), (unsigned)N);
   global_maxpool_kernel<<<grid, 128, 0, s>>>(x, y, S, C);
+  IBL_CUDA_OK(cudaGetLastError());
+  return IBL_OK;
+}
+
+__global__ void global_maxpool_planes_kernel(const __nv_bfloat16* __restrict__ hi,
+                                             const __nv_bfloat16* __restrict__ lo, int S, int C,
+                                             float* __restrict__ y) {
+  const long long n = blockIdx.y;
+  const int c = blockIdx.x * blockDim.x + threadIdx.x;
+  if (c >= C) return;
+  float m = -INFINITY;
+  const long long base = n * S * (long long)C + c;
+  for (int s = 0; s < S; ++s) {
+    const long long o = base + (long long)s * C;
+    m = fmaxf(m, __bfloat162float(hi[o]) + __bfloat162float(lo[o]));
+  }
+  y[n * C + c] = m;
+}
+int launch_global_maxpool_planes(const __nv_bfloat16* hi, const __nv_bfloat16* lo, int N, int S, int C, float* y,
+                                 cudaStream_t s) {
+  dim3 grid((unsigned)cdiv(C, 128), (unsigned)N);
+  global_maxpool_planes_kernel<<<grid, 128, 0, s>>>(hi, lo, S, C, y);
   IBL_CUDA_OK(cudaGetLastError());
   return IBL_OK;
 }

@@ -18,6 +18,8 @@
 // Two TMEM accumulator buffers let the epilogue of tile i overlap the main loop of tile i+1.
 // Epilogue: TMEM -> registers, + bias, ReLU, optional fused 2x2 max-pool (warp shuffles),
 // split into hi/lo planes (or fp32 for conv5_3), 16-byte stores.
+#include <stdlib.h>
+
 #include "common.cuh"
 #include "tc_common.cuh"
 
@@ -83,6 +85,8 @@ struct ConvTcArgs {
   __nv_bfloat16* y_hi;
   __nv_bfloat16* y_lo;
   float* y_f32;
+  float* ssq;             // optional [n_tiles][N*H*W] per-pixel sum of squares of the outputs (no pool)
+  long long ssq_stride;
 };
 
 constexpr int TC_BM = 128;
@@ -244,6 +248,7 @@ conv3x3_tc_kernel(const __grid_constant__ CUtensorMap tm_xhi, const __grid_const
       mbar_wait(&tfull_bar[as], aphase);
       tc_fence_after();
       const uint32_t t_row = tmem_base + ((uint32_t)(q * 32) << 16) + as * BN;
+      float ssq_acc = 0.f;   // per-pixel sum of squares over this N tile (feeds NetVLAD's input norm)
 #pragma unroll 1
       for (int ch = 0; ch < BN / 32; ++ch) {
         uint32_t raw[32];
@@ -262,6 +267,10 @@ conv3x3_tc_kernel(const __grid_constant__ CUtensorMap tm_xhi, const __grid_const
         if (a.relu) {
 #pragma unroll
           for (int j = 0; j < 32; ++j) v[j] = fmaxf(v[j], 0.f);
+        }
+        if (a.ssq) {
+#pragma unroll
+          for (int j = 0; j < 32; ++j) ssq_acc = fmaf(v[j], v[j], ssq_acc);
         }
         if (a.pool) {
 #pragma unroll
@@ -296,6 +305,7 @@ conv3x3_tc_kernel(const __grid_constant__ CUtensorMap tm_xhi, const __grid_const
           }
         }
       }
+      if (a.ssq && valid && !a.pool) a.ssq[(long long)nt * a.ssq_stride + pix] = ssq_acc;
       tc_fence_before();
       __syncwarp();
       if (lane == 0) mbar_arrive(&tempty_bar[as]);
@@ -335,7 +345,8 @@ void tc_set_bn_override(int bn) { g_tc_bn_override = bn; }
 
 int launch_conv3x3_tc(const __nv_bfloat16* x_hi, const __nv_bfloat16* x_lo, const ConvParams& p,
                       int N, int H, int W, int cin, int cout, bool relu, bool pool,
-                      __nv_bfloat16* y_hi, __nv_bfloat16* y_lo, float* y_f32, cudaStream_t s) {
+                      __nv_bfloat16* y_hi, __nv_bfloat16* y_lo, float* y_f32, cudaStream_t s, float* ssq,
+                      int* ssq_parts) {
   IBL_REQUIRE(cin % 64 == 0 && cout % 64 == 0, "tcgen05 conv needs Cin%64==0 and Cout%64==0");
   IBL_REQUIRE(p.w_hi && p.w_lo, "tcgen05 conv: weights were not re-laid-out");
   IBL_REQUIRE(H >= 1 && W >= 1 && N >= 1, "empty conv input");
@@ -350,12 +361,24 @@ int launch_conv3x3_tc(const __nv_bfloat16* x_hi, const __nv_bfloat16* x_lo, cons
   const int TW = 1 << a.tw_log2, TH = 128 / TW;
   a.tiles_w = cdiv(W, TW);
   a.tiles_h = cdiv(H, TH);
+  // N tile: 256 where Cout allows and there are enough patches to fill the machine (measured
+  // 5-9 % faster than 128 on conv3_x/conv4_x: 96 vs 128 B/clk of shared-memory operand reads per
+  // MMA); 128 otherwise; 64 only for Cout = 64 (profiles/r01_bench_layers_v1.txt).
   int bn = cout % 128 == 0 ? 128 : 64;
+  if (cout % 256 == 0 && (long long)N * a.tiles_h * a.tiles_w * (cout / 256) >= 4 * 148) bn = 256;
   if (g_tc_bn_override && cout % g_tc_bn_override == 0) bn = g_tc_bn_override;
+  {
+    static int env_bn = -1;   // experiment hook: IBL_TC_BN=256 forces the N tile where it divides Cout
+    if (env_bn < 0) { const char* v = getenv("IBL_TC_BN"); env_bn = v ? atoi(v) : 0; }
+    if (env_bn > 0 && !g_tc_bn_override && cout % env_bn == 0) bn = env_bn;
+  }
   a.n_tiles = cout / bn;
   a.total_tiles = N * a.tiles_h * a.tiles_w * a.n_tiles;
   a.relu = relu; a.pool = pool;
   a.bias = p.bias; a.y_hi = y_hi; a.y_lo = y_lo; a.y_f32 = y_f32;
+  a.ssq = pool ? nullptr : ssq;
+  a.ssq_stride = (long long)N * H * W;
+  if (ssq_parts) *ssq_parts = a.n_tiles;
 
   CUtensorMap m_xhi, m_xlo, m_whi, m_wlo;
   {

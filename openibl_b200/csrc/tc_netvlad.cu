@@ -1,0 +1,538 @@
+// tcgen05 building block for the fused NetVLAD kernel: a "TN" product  C[m,n] = sum_k A[k,m] B[k,n]
+// whose operands are MN-major in shared memory (the reduction index is the row index), i.e. the layout
+// a TMA box [rows = k][64 contiguous elements] produces.  This is what the second NetVLAD contraction
+// needs: vlad[c,k] = sum_s x^[s,c] a[s,k] reads the same [pixel][channel] tile the first contraction
+// (logits = x^ W^T, K-major) already staged, so the feature map is read from HBM once.
+#include "common.cuh"
+#include "tc_common.cuh"
+
+namespace ibl {
+
+using namespace tc;
+
+// MN-major operand, 128-byte swizzle: rows (K index) of 64 bf16 = 128 B, 8-row atoms 1024 B apart
+// (SBO); further 64-element blocks along M/N are `lbo_bytes` apart (cute::UMMA canonical layout
+// ((8,n),(8,k)):((1,LBO),(8,SBO)) in 16-byte units).
+__device__ __forceinline__ uint64_t umma_desc_mnmajor_sw128(uint32_t smem_addr, uint32_t lbo_bytes) {
+  uint64_t d = 0;
+  d |= (uint64_t)((smem_addr >> 4) & 0x3fffu);
+  d |= (uint64_t)((lbo_bytes >> 4) & 0x3fffu) << 16;
+  d |= (uint64_t)(1024u >> 4) << 32;
+  d |= (uint64_t)1 << 46;
+  d |= (uint64_t)2 << 61;
+  return d;
+}
+__host__ __device__ constexpr uint32_t umma_idesc_bf16_f32_mn(int M, int N, int a_mn, int b_mn) {
+  return umma_idesc_bf16_f32(M, N) | ((uint32_t)a_mn << 15) | ((uint32_t)b_mn << 16);
+}
+
+// ---- micro-test: one CTA, M = 128, N = 64, K = 128, bf16x3 -----------------------------------------
+__global__ void __launch_bounds__(128, 1)
+tn_gemm_test_kernel(const __grid_constant__ CUtensorMap tm_ahi, const __grid_constant__ CUtensorMap tm_alo,
+                    const __grid_constant__ CUtensorMap tm_bhi, const __grid_constant__ CUtensorMap tm_blo,
+                    float* __restrict__ C) {
+  extern __shared__ __align__(1024) uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  // A_hi: two [128 k][64 m] blocks (32 KB), A_lo (32 KB), B_hi [128 k][64 n] (16 KB), B_lo (16 KB)
+  uint8_t* a_hi = smem;
+  uint8_t* a_lo = smem + 32768;
+  uint8_t* b_hi = smem + 65536;
+  uint8_t* b_lo = smem + 81920;
+  uint64_t* bars = reinterpret_cast<uint64_t*>(smem + 98304);
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 2);
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  if (threadIdx.x == 0) {
+    mbar_init(&bars[0], 1);
+    mbar_init(&bars[1], 1);
+    fence_barrier_init();
+    fence_proxy_async();
+  }
+  if (warp == 0) {
+    tmem_alloc(tmem_slot, 64);
+    tmem_relinquish();
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+  if (threadIdx.x == 0) {
+    mbar_arrive_expect_tx(&bars[0], 98304);
+    tma_load_2d(a_hi, &tm_ahi, &bars[0], 0, 0);
+    tma_load_2d(a_hi + 16384, &tm_ahi, &bars[0], 64, 0);
+    tma_load_2d(a_lo, &tm_alo, &bars[0], 0, 0);
+    tma_load_2d(a_lo + 16384, &tm_alo, &bars[0], 64, 0);
+    tma_load_2d(b_hi, &tm_bhi, &bars[0], 0, 0);
+    tma_load_2d(b_lo, &tm_blo, &bars[0], 0, 0);
+    mbar_wait(&bars[0], 0);
+    tc_fence_after();
+    constexpr uint32_t idesc = umma_idesc_bf16_f32_mn(128, 64, 1, 1);
+    for (int ks = 0; ks < 8; ++ks) {   // 16 k-rows (2048 B) per MMA
+      const uint32_t off = ks * 2048;
+      const uint64_t dah = umma_desc_mnmajor_sw128(smem_u32(a_hi) + off, 16384);
+      const uint64_t dal = umma_desc_mnmajor_sw128(smem_u32(a_lo) + off, 16384);
+      const uint64_t dbh = umma_desc_mnmajor_sw128(smem_u32(b_hi) + off, 0);
+      const uint64_t dbl = umma_desc_mnmajor_sw128(smem_u32(b_lo) + off, 0);
+      umma_bf16(tmem_base, dal, dbh, idesc, ks > 0 ? 1u : 0u);
+      umma_bf16(tmem_base, dah, dbl, idesc, 1u);
+      umma_bf16(tmem_base, dah, dbh, idesc, 1u);
+    }
+    umma_commit(&bars[1]);
+  }
+  __syncwarp();
+  mbar_wait(&bars[1], 0);
+  tc_fence_after();
+  const int m = warp * 32 + lane;
+  for (int ch = 0; ch < 2; ++ch) {
+    uint32_t raw[32];
+    tmem_ld_32x32(tmem_base + ((uint32_t)(warp * 32) << 16) + ch * 32, raw);
+    tmem_ld_wait();
+#pragma unroll
+    for (int j = 0; j < 32; ++j) C[m * 64 + ch * 32 + j] = __uint_as_float(raw[j]);
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 0) {
+    tc_fence_after();
+    tmem_dealloc(tmem_base, 64);
+  }
+}
+
+// A [128 k][128 m] fp32, B [128 k][64 n] fp32 (device) -> C [128 m][64 n] = A^T B
+int debug_gemm_tn(const float* A, const float* B, float* C, cudaStream_t s) {
+  __nv_bfloat16 *pa = nullptr, *pb = nullptr;
+  IBL_CUDA_OK(cudaMalloc(&pa, 128 * 128 * 2 * 2));
+  IBL_CUDA_OK(cudaMalloc(&pb, 128 * 64 * 2 * 2));
+  int rc = launch_f32_to_planes(A, 128 * 128, pa, pa + 128 * 128, s);
+  if (rc == IBL_OK) rc = launch_f32_to_planes(B, 128 * 64, pb, pb + 128 * 64, s);
+  CUtensorMap maps[4];
+  uint64_t da[2] = {128, 128}, db[2] = {64, 128}, sa[1] = {128 * 2}, sb[1] = {64 * 2};
+  uint32_t box[2] = {64, 128};
+  if (rc == IBL_OK) rc = make_tmap(&maps[0], CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, pa, da, sa, box);
+  if (rc == IBL_OK) rc = make_tmap(&maps[1], CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, pa + 128 * 128, da, sa, box);
+  if (rc == IBL_OK) rc = make_tmap(&maps[2], CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, pb, db, sb, box);
+  if (rc == IBL_OK) rc = make_tmap(&maps[3], CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, pb + 128 * 64, db, sb, box);
+  if (rc == IBL_OK) {
+    const int smem = 98304 + 1024 + 64;
+    cudaFuncSetAttribute(tn_gemm_test_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
+    tn_gemm_test_kernel<<<1, 128, smem, s>>>(maps[0], maps[1], maps[2], maps[3], C);
+    if (cudaGetLastError() != cudaSuccess) rc = IBL_ERR_CUDA;
+  }
+  cudaError_t ce = cudaStreamSynchronize(s);
+  cudaFree(pa);
+  cudaFree(pb);
+  if (rc == IBL_OK && ce != cudaSuccess) { set_last_error(cudaGetErrorString(ce)); rc = IBL_ERR_CUDA; }
+  return rc;
+}
+
+// =====================================================================================================
+// Fused NetVLAD (reference ibl/models/netvlad.py:44-61 + the intra-normalisation / L2 of :78-80)
+//
+//   x^[s,:] = x[s,:] / max(|x[s,:]|, eps)                       |x[s,:]|^2 comes from the conv5_3 epilogue
+//   z[s,k]  = W[k,:] . x^[s,:]          GEMM 1 (tcgen05, K-major operands: pixel tile x channel chunk)
+//   a[s,:]  = softmax_k z[s,:]          epilogue warps, one pixel per thread, fp32, max-subtracted
+//   V[c,k]  = sum_s x^[s,c] a[s,k]      GEMM 2 (tcgen05, MN-major operands: the SAME [pixel][channel]
+//                                       tiles, and a' = a/|x| written to shared memory by the softmax)
+//   vlad[k,c] = V[c,k] - cent[k,c] * sum_s a[s,k]
+//
+// One work unit = (image, every G-th 128-pixel tile); a unit keeps V (512 x 64 fp32 = 256 TMEM columns)
+// resident across its tiles and writes one partial; `netvlad_finalize_kernel` adds the G partials,
+// subtracts the centroid term and applies the two normalisations.  The feature map is read from HBM
+// once (the second pass over a tile's channel chunks hits L2).  Both contractions are bf16x3.
+//
+// Warp roles: warp 0 TMA producer, warp 1 MMA issuer + TMEM owner, warps 2-5 softmax / epilogue.
+// Shared memory: 3 stages of 64 KiB (GEMM 1 stage: X_hi | X_lo | W_hi,W_lo of one 64-channel chunk;
+// GEMM 2 stage: X_hi c0 | X_hi c1 | X_lo c0 | X_lo c1 of one 128-channel block) + a' hi/lo (32 KiB).
+// =====================================================================================================
+struct NvTcArgs {
+  int B, S, G, T;                 // images, pixels per image, units per image, 128-pixel tiles per image
+  int ssq_parts;                  // number of partial |x|^2 planes to add
+  const float* ssq;               // [ssq_parts][B*S]
+  int normalize_input;
+  float* part;                    // [B*G][64][512]   partial V^T (k-major rows, c contiguous)
+  float* asum_part;               // [B*G][64]
+};
+
+constexpr int NV_STAGE = 65536, NV_NSTAGE = 3, NV_SLOT = 16384;
+
+__global__ void __launch_bounds__(192, 1)
+netvlad_tc_kernel(const __grid_constant__ CUtensorMap tm_xhi, const __grid_constant__ CUtensorMap tm_xlo,
+                  const __grid_constant__ CUtensorMap tm_whi, const __grid_constant__ CUtensorMap tm_wlo,
+                  const NvTcArgs a) {
+  extern __shared__ __align__(1024) uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  uint8_t* asm_hi = smem + NV_NSTAGE * NV_STAGE;
+  uint8_t* asm_lo = asm_hi + NV_SLOT;
+  uint64_t* bars = reinterpret_cast<uint64_t*>(asm_lo + NV_SLOT);
+  uint64_t* full_bar = bars;                 // [3]
+  uint64_t* empty_bar = bars + 3;            // [3]
+  uint64_t* z_full = bars + 6;
+  uint64_t* a_full = bars + 7;
+  uint64_t* a_empty = bars + 8;
+  uint64_t* d_full = bars + 9;
+  uint64_t* d_empty = bars + 10;
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 11);
+  float* asum_sm = reinterpret_cast<float*>(bars + 12);   // [4 warps][64]
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  if (warp == 0 && lane == 0) {
+    tma_prefetch_desc(&tm_xhi); tma_prefetch_desc(&tm_xlo); tma_prefetch_desc(&tm_whi); tma_prefetch_desc(&tm_wlo);
+    for (int i = 0; i < 3; ++i) { mbar_init(&full_bar[i], 1); mbar_init(&empty_bar[i], 1); }
+    mbar_init(z_full, 1);
+    mbar_init(a_full, 4);
+    mbar_init(a_empty, 1);
+    mbar_init(d_full, 1);
+    mbar_init(d_empty, 4);
+    fence_barrier_init();
+    fence_proxy_async();
+  }
+  if (warp == 1) { tmem_alloc(tmem_slot, 512); tmem_relinquish(); }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+  const uint32_t t_z = tmem_base, t_d = tmem_base + 64;
+  const int n_units = a.B * a.G;
+
+  if (warp == 0) {
+    if (lane == 0) {
+      int stage = 0; uint32_t phase = 0;
+      for (int unit = blockIdx.x; unit < n_units; unit += gridDim.x) {
+        const int b = unit / a.G, g = unit - b * a.G;
+        for (int t = g; t < a.T; t += a.G) {
+          const int p0 = t * 128;
+          for (int c = 0; c < 8; ++c) {          // GEMM 1 stages: one 64-channel chunk + its W chunk
+            mbar_wait(&empty_bar[stage], phase ^ 1);
+            uint8_t* st = smem + stage * NV_STAGE;
+            mbar_arrive_expect_tx(&full_bar[stage], 3 * NV_SLOT);
+            tma_load_3d(st, &tm_xhi, &full_bar[stage], c * 64, p0, b);
+            tma_load_3d(st + NV_SLOT, &tm_xlo, &full_bar[stage], c * 64, p0, b);
+            tma_load_2d(st + 2 * NV_SLOT, &tm_whi, &full_bar[stage], c * 64, 0);
+            tma_load_2d(st + 2 * NV_SLOT + 8192, &tm_wlo, &full_bar[stage], c * 64, 0);
+            if (++stage == NV_NSTAGE) { stage = 0; phase ^= 1; }
+          }
+          for (int cb = 0; cb < 4; ++cb) {       // GEMM 2 stages: one 128-channel block (L2 hits)
+            mbar_wait(&empty_bar[stage], phase ^ 1);
+            uint8_t* st = smem + stage * NV_STAGE;
+            mbar_arrive_expect_tx(&full_bar[stage], 4 * NV_SLOT);
+            tma_load_3d(st, &tm_xhi, &full_bar[stage], cb * 128, p0, b);
+            tma_load_3d(st + NV_SLOT, &tm_xhi, &full_bar[stage], cb * 128 + 64, p0, b);
+            tma_load_3d(st + 2 * NV_SLOT, &tm_xlo, &full_bar[stage], cb * 128, p0, b);
+            tma_load_3d(st + 3 * NV_SLOT, &tm_xlo, &full_bar[stage], cb * 128 + 64, p0, b);
+            if (++stage == NV_NSTAGE) { stage = 0; phase ^= 1; }
+          }
+        }
+      }
+    }
+  } else if (warp == 1) {
+    if (lane == 0) {
+      constexpr uint32_t idesc1 = umma_idesc_bf16_f32(128, 64);
+      constexpr uint32_t idesc2 = umma_idesc_bf16_f32_mn(128, 64, 1, 1);
+      int stage = 0; uint32_t phase = 0;
+      int it = 0, u = 0;
+      for (int unit = blockIdx.x; unit < n_units; unit += gridDim.x, ++u) {
+        const int b = unit / a.G, g = unit - b * a.G;
+        (void)b;
+        mbar_wait(d_empty, (u & 1) ^ 1);         // previous unit's partial has been read out of TMEM
+        tc_fence_after();
+        bool first_tile = true;
+        for (int t = g; t < a.T; t += a.G, ++it) {
+          // ---- GEMM 1: Z[128 px, 64 k] ----
+          for (int c = 0; c < 8; ++c) {
+            mbar_wait(&full_bar[stage], phase);
+            tc_fence_after();
+            const uint32_t sa = smem_u32(smem + stage * NV_STAGE);
+            const uint64_t xh = umma_desc_kmajor_sw128(sa), xl = umma_desc_kmajor_sw128(sa + NV_SLOT);
+            const uint64_t wh = umma_desc_kmajor_sw128(sa + 2 * NV_SLOT);
+            const uint64_t wl = umma_desc_kmajor_sw128(sa + 2 * NV_SLOT + 8192);
+#pragma unroll
+            for (int k = 0; k < 4; ++k) {
+              const uint64_t ko = (uint64_t)(k * 2);
+              umma_bf16(t_z, xl + ko, wh + ko, idesc1, (c > 0 || k > 0) ? 1u : 0u);
+              umma_bf16(t_z, xh + ko, wl + ko, idesc1, 1u);
+              umma_bf16(t_z, xh + ko, wh + ko, idesc1, 1u);
+            }
+            umma_commit(&empty_bar[stage]);
+            if (++stage == NV_NSTAGE) { stage = 0; phase ^= 1; }
+          }
+          umma_commit(z_full);
+          // ---- GEMM 2: V[128 c, 64 k] (4 channel blocks) += X^T a' ----
+          mbar_wait(a_full, it & 1);
+          tc_fence_after();
+          const uint32_t ah = smem_u32(asm_hi), al = smem_u32(asm_lo);
+          for (int cb = 0; cb < 4; ++cb) {
+            mbar_wait(&full_bar[stage], phase);
+            tc_fence_after();
+            const uint32_t sa = smem_u32(smem + stage * NV_STAGE);
+#pragma unroll
+            for (int ks = 0; ks < 8; ++ks) {     // 16 pixel rows (2048 B) per MMA
+              const uint32_t off = ks * 2048;
+              const uint64_t xh = umma_desc_mnmajor_sw128(sa + off, NV_SLOT);
+              const uint64_t xl = umma_desc_mnmajor_sw128(sa + 2 * NV_SLOT + off, NV_SLOT);
+              const uint64_t bh = umma_desc_mnmajor_sw128(ah + off, 0);
+              const uint64_t bl = umma_desc_mnmajor_sw128(al + off, 0);
+              const uint32_t d = t_d + cb * 64;
+              umma_bf16(d, xl, bh, idesc2, (first_tile && ks == 0) ? 0u : 1u);
+              umma_bf16(d, xh, bl, idesc2, 1u);
+              umma_bf16(d, xh, bh, idesc2, 1u);
+            }
+            umma_commit(&empty_bar[stage]);
+            if (++stage == NV_NSTAGE) { stage = 0; phase ^= 1; }
+          }
+          umma_commit(a_empty);                  // a' buffer (and Z) may be overwritten
+          first_tile = false;
+        }
+        umma_commit(d_full);
+      }
+    }
+  } else {
+    const int q = warp & 3;
+    const int s_loc = q * 32 + lane;             // pixel row inside the tile == TMEM lane
+    const uint32_t lane_base = (uint32_t)(q * 32) << 16;
+    int it = 0, u = 0;
+    for (int unit = blockIdx.x; unit < n_units; unit += gridDim.x, ++u) {
+      const int b = unit / a.G, g = unit - b * a.G;
+      float as0 = 0.f, as1 = 0.f;                // sum_s a[s,k] for k = 2*lane, 2*lane+1 (this warp's rows)
+      for (int t = g; t < a.T; t += a.G, ++it) {
+        const int s = t * 128 + s_loc;
+        const bool valid = s < a.S;
+        float inv = 1.f;
+        if (valid && a.normalize_input) {
+          float ss = 0.f;
+          for (int p = 0; p < a.ssq_parts; ++p) ss += __ldg(a.ssq + (long long)p * a.B * a.S + (long long)b * a.S + s);
+          inv = 1.f / fmaxf(sqrtf(ss), 1e-12f);
+        }
+        mbar_wait(z_full, it & 1);
+        tc_fence_after();
+        float z[64];
+        {
+          uint32_t r0[32], r1[32];
+          tmem_ld_32x32(t_z + lane_base, r0);
+          tmem_ld_32x32(t_z + lane_base + 32, r1);
+          tmem_ld_wait();
+#pragma unroll
+          for (int j = 0; j < 32; ++j) { z[j] = __uint_as_float(r0[j]) * inv; z[32 + j] = __uint_as_float(r1[j]) * inv; }
+        }
+        float m = z[0];
+#pragma unroll
+        for (int j = 1; j < 64; ++j) m = fmaxf(m, z[j]);
+        float sum = 0.f;
+#pragma unroll
+        for (int j = 0; j < 64; ++j) { z[j] = expf(z[j] - m); sum += z[j]; }
+        const float rs = valid ? 1.f / sum : 0.f;
+#pragma unroll
+        for (int j = 0; j < 64; ++j) z[j] *= rs;   // a[s,:] (0 for rows past the image)
+        // a' = a * inv as bf16 hi/lo, MN-major SW128 row s_loc: 8 chunks of 8 values, chunk j at j^(s&7)
+        mbar_wait(a_empty, (it & 1) ^ 1);          // GEMM 2 of the previous tile has consumed the buffer
+        {
+          uint8_t* rh = asm_hi + s_loc * 128;
+          uint8_t* rl = asm_lo + s_loc * 128;
+#pragma unroll
+          for (int j = 0; j < 8; ++j) {
+            uint32_t hi[4], lo[4];
+#pragma unroll
+            for (int e = 0; e < 4; ++e) {
+              const float x0 = z[8 * j + 2 * e] * inv, x1 = z[8 * j + 2 * e + 1] * inv;
+              const __nv_bfloat16 h0 = __float2bfloat16_rn(x0), h1 = __float2bfloat16_rn(x1);
+              __nv_bfloat162 hh(h0, h1);
+              __nv_bfloat162 ll = __floats2bfloat162_rn(x0 - __bfloat162float(h0), x1 - __bfloat162float(h1));
+              hi[e] = *reinterpret_cast<uint32_t*>(&hh);
+              lo[e] = *reinterpret_cast<uint32_t*>(&ll);
+            }
+            const int pos = (j ^ (s_loc & 7)) * 16;
+            *reinterpret_cast<uint4*>(rh + pos) = make_uint4(hi[0], hi[1], hi[2], hi[3]);
+            *reinterpret_cast<uint4*>(rl + pos) = make_uint4(lo[0], lo[1], lo[2], lo[3]);
+          }
+        }
+        fence_proxy_async();                       // generic-proxy smem writes -> visible to the tensor core
+        tc_fence_before();
+        __syncwarp();
+        if (lane == 0) mbar_arrive(a_full);
+        // column sums of a over this warp's 32 rows: butterfly, lane L ends with columns 2L, 2L+1
+        {
+          float w32[32];
+#pragma unroll
+          for (int i = 0; i < 32; ++i) {
+            const float keep = (lane & 16) ? z[32 + i] : z[i];
+            const float send = (lane & 16) ? z[i] : z[32 + i];
+            w32[i] = keep + __shfl_xor_sync(0xffffffffu, send, 16);
+          }
+          float w16[16];
+#pragma unroll
+          for (int i = 0; i < 16; ++i) {
+            const float keep = (lane & 8) ? w32[16 + i] : w32[i];
+            const float send = (lane & 8) ? w32[i] : w32[16 + i];
+            w16[i] = keep + __shfl_xor_sync(0xffffffffu, send, 8);
+          }
+          float w8[8];
+#pragma unroll
+          for (int i = 0; i < 8; ++i) {
+            const float keep = (lane & 4) ? w16[8 + i] : w16[i];
+            const float send = (lane & 4) ? w16[i] : w16[8 + i];
+            w8[i] = keep + __shfl_xor_sync(0xffffffffu, send, 4);
+          }
+          float w4[4];
+#pragma unroll
+          for (int i = 0; i < 4; ++i) {
+            const float keep = (lane & 2) ? w8[4 + i] : w8[i];
+            const float send = (lane & 2) ? w8[i] : w8[4 + i];
+            w4[i] = keep + __shfl_xor_sync(0xffffffffu, send, 2);
+          }
+#pragma unroll
+          for (int i = 0; i < 2; ++i) {
+            const float keep = (lane & 1) ? w4[2 + i] : w4[i];
+            const float send = (lane & 1) ? w4[i] : w4[2 + i];
+            const float v = keep + __shfl_xor_sync(0xffffffffu, send, 1);
+            if (i == 0) as0 += v; else as1 += v;
+          }
+        }
+      }
+      // ---- unit epilogue: partial V^T and partial sum_s a ----
+      asum_sm[q * 64 + 2 * lane] = as0;
+      asum_sm[q * 64 + 2 * lane + 1] = as1;
+      mbar_wait(d_full, u & 1);
+      tc_fence_after();
+      float* po = a.part + (long long)unit * 64 * 512;
+      for (int cb = 0; cb < 4; ++cb) {
+        uint32_t r0[32], r1[32];
+        tmem_ld_32x32(t_d + cb * 64 + lane_base, r0);
+        tmem_ld_32x32(t_d + cb * 64 + lane_base + 32, r1);
+        tmem_ld_wait();
+        const int c = cb * 128 + s_loc;            // TMEM lane == channel inside the block
+#pragma unroll
+        for (int k = 0; k < 32; ++k) {
+          po[(long long)k * 512 + c] = __uint_as_float(r0[k]);
+          po[(long long)(k + 32) * 512 + c] = __uint_as_float(r1[k]);
+        }
+      }
+      tc_fence_before();
+      // the four epilogue warps meet (named barrier 1) before their asum partials are combined
+      asm volatile("bar.sync 1, 128;" ::: "memory");
+      if (threadIdx.x - 64 < 64) {
+        const int k = threadIdx.x - 64;
+        a.asum_part[(long long)unit * 64 + k] = asum_sm[k] + asum_sm[64 + k] + asum_sm[128 + k] + asum_sm[192 + k];
+      }
+      asm volatile("bar.sync 1, 128;" ::: "memory");
+      if (lane == 0) mbar_arrive(d_empty);
+    }
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 1) { tc_fence_after(); tmem_dealloc(tmem_base, 512); }
+}
+
+// vlad[k,c] = sum_g part[b,g,k,c] - cent[k,c] * sum_g asum[b,g,k]; intra-normalise, flatten, L2
+__global__ void __launch_bounds__(256)
+netvlad_finalize_kernel(const float* __restrict__ part, const float* __restrict__ asum_part, int G,
+                        const float* __restrict__ cent, float* __restrict__ vlad_raw /*nullable*/,
+                        float* __restrict__ vlad_norm /*nullable*/) {
+  __shared__ float row_inv[64], row_ss[64], asum[64];
+  __shared__ float ginv_s;
+  const long long b = blockIdx.x;
+  const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+  if (threadIdx.x < 64) {
+    float s = 0.f;
+    for (int g = 0; g < G; ++g) s += asum_part[(b * G + g) * 64 + threadIdx.x];
+    asum[threadIdx.x] = s;
+  }
+  __syncthreads();
+  // each warp owns 8 cluster rows; a lane holds 16 channels of the row in registers
+  for (int k = wid * 8; k < wid * 8 + 8; ++k) {
+    float v[16];
+    float ss = 0.f;
+#pragma unroll
+    for (int j = 0; j < 16; ++j) {
+      const int c = lane + 32 * j;
+      float acc = 0.f;
+      for (int g = 0; g < G; ++g) acc += part[((b * G + g) * 64 + k) * 512 + c];
+      acc -= __ldg(cent + k * 512 + c) * asum[k];
+      v[j] = acc;
+      ss = fmaf(acc, acc, ss);
+    }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) ss += __shfl_xor_sync(0xffffffffu, ss, o);
+    const float inv = 1.f / fmaxf(sqrtf(ss), 1e-12f);
+    float s2 = 0.f;
+#pragma unroll
+    for (int j = 0; j < 16; ++j) {
+      const int c = lane + 32 * j;
+      if (vlad_raw) vlad_raw[(b * 64 + k) * 512 + c] = v[j];
+      const float w = v[j] * inv;
+      s2 = fmaf(w, w, s2);
+      if (vlad_norm) vlad_norm[(b * 64 + k) * 512 + c] = w;     // scaled by the global norm below
+    }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) s2 += __shfl_xor_sync(0xffffffffu, s2, o);
+    if (lane == 0) { row_inv[k] = inv; row_ss[k] = s2; }
+  }
+  __syncthreads();
+  if (!vlad_norm) return;
+  if (threadIdx.x < 32) {
+    float tot = row_ss[lane] + row_ss[lane + 32];
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) tot += __shfl_xor_sync(0xffffffffu, tot, o);
+    if (lane == 0) ginv_s = 1.f / fmaxf(sqrtf(tot), 1e-12f);
+  }
+  __syncthreads();
+  const float ginv = ginv_s;
+  float4* o = reinterpret_cast<float4*>(vlad_norm + b * 64 * 512);
+  for (int e = threadIdx.x; e < 64 * 512 / 4; e += 256) {
+    float4 w = o[e];
+    w.x *= ginv; w.y *= ginv; w.z *= ginv; w.w *= ginv;
+    o[e] = w;
+  }
+}
+
+int netvlad_tc_units(int B, int S) {
+  int sms = 148;
+  int dev = 0;
+  cudaGetDevice(&dev);
+  cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+  const int T = cdiv(S, 128);
+  int G = sms / (B > 0 ? B : 1);
+  if (G < 1) G = 1;
+  if (G > T) G = T;
+  return G;
+}
+
+// x planes [B,S,512] (hi, lo), w planes [64,512] (hi, lo), ssq [parts][B*S], cent [64,512] fp32
+int launch_netvlad_tc(const __nv_bfloat16* x_hi, const __nv_bfloat16* x_lo, int B, int S,
+                      const __nv_bfloat16* w_hi, const __nv_bfloat16* w_lo, const float* ssq, int ssq_parts,
+                      const float* cent, bool normalize_input, float* part, float* asum_part,
+                      float* vlad_raw, float* vlad_norm, cudaStream_t s) {
+  CUtensorMap mx_hi, mx_lo, mw_hi, mw_lo;
+  {
+    uint64_t dims[3] = {512, (uint64_t)S, (uint64_t)B};
+    uint64_t str[2] = {512 * 2, (uint64_t)S * 512 * 2};
+    uint32_t box[3] = {64, 128, 1};
+    IBL_RET(make_tmap(&mx_hi, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 3, x_hi, dims, str, box));
+    IBL_RET(make_tmap(&mx_lo, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 3, x_lo, dims, str, box));
+  }
+  {
+    uint64_t dims[2] = {512, 64};
+    uint64_t str[1] = {512 * 2};
+    uint32_t box[2] = {64, 64};
+    IBL_RET(make_tmap(&mw_hi, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, w_hi, dims, str, box));
+    IBL_RET(make_tmap(&mw_lo, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, w_lo, dims, str, box));
+  }
+  NvTcArgs a{};
+  a.B = B; a.S = S; a.T = cdiv(S, 128); a.G = netvlad_tc_units(B, S);
+  a.ssq = ssq; a.ssq_parts = ssq_parts; a.normalize_input = normalize_input ? 1 : 0;
+  a.part = part; a.asum_part = asum_part;
+  const int smem = NV_NSTAGE * NV_STAGE + 2 * NV_SLOT + 1024 + 128 + 4 * 64 * 4;
+  static bool attr_done = false;
+  if (!attr_done) {
+    IBL_CUDA_OK(cudaFuncSetAttribute(netvlad_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
+    attr_done = true;
+  }
+  int sms = 148, dev = 0;
+  cudaGetDevice(&dev);
+  cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+  const int units = B * a.G;
+  netvlad_tc_kernel<<<units < sms ? units : sms, 192, smem, s>>>(mx_hi, mx_lo, mw_hi, mw_lo, a);
+  IBL_CUDA_OK(cudaGetLastError());
+  netvlad_finalize_kernel<<<B, 256, 0, s>>>(part, asum_part, a.G, cent, vlad_raw, vlad_norm);
+  IBL_CUDA_OK(cudaGetLastError());
+  return IBL_OK;
+}
+
+}  // namespace ibl

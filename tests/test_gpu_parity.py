@@ -214,6 +214,20 @@ def test_netvlad_ragged_sizes_vs_oracle(eng, O):
                                        want_raw=True, want_norm=True)
         assert rel_l2(raw.cpu(), want) < 2e-5, (N, h, w)
         assert rel_l2(nrm.cpu(), O.vlad_normalize(want)) < 2e-5
+        # NHWC input takes the fused tcgen05 kernel (partial last tile, S < 128, several units per image)
+        for mode in (1, 0):
+            eng.set_gemm_mode(mode)
+            raw2, nrm2 = eng.netvlad_forward(feat.permute(0, 2, 3, 1).contiguous().cuda(), p["conv_weight"].cuda(),
+                                             p["centroids"].cuda(), nhwc=True, want_raw=True, want_norm=True)
+            assert rel_l2(raw2.cpu(), want) < 3e-5, (N, h, w, mode)
+            assert rel_l2(nrm2.cpu(), O.vlad_normalize(want)) < 3e-5, (N, h, w, mode)
+    # a full batch: 32 images x 1200 pixels -> 4 units per image on 128 CTAs
+    feat = torch.randn(32, 30, 40, 512, generator=gen)
+    want = O.netvlad(feat.permute(0, 3, 1, 2), p["conv_weight"], p["centroids"])
+    eng.set_gemm_mode(1)
+    _, nrm = eng.netvlad_forward(feat.cuda(), p["conv_weight"].cuda(), p["centroids"].cuda(), nhwc=True,
+                                 want_raw=False, want_norm=True)
+    assert rel_l2(nrm.cpu(), O.vlad_normalize(want)) < 3e-5
 
 
 # ---------------------------------------------------------------------------------------------
