@@ -79,6 +79,9 @@ int launch_conv3x3_tc(const __nv_bfloat16* x_hi, const __nv_bfloat16* x_lo, cons
 int launch_maxpool2x2_planes(const __nv_bfloat16* hi, const __nv_bfloat16* lo, int N, int H, int W,
                              int C, __nv_bfloat16* yhi, __nv_bfloat16* ylo, cudaStream_t s);
 int tc_selftest(float* max_rel_err, cudaStream_t s);
+// tc_conv1.cu
+int launch_conv1_1_tc(const float* x_nchw, const float* w_oihw, const float* bias, int N, int H, int W,
+                      __nv_bfloat16* y_hi, __nv_bfloat16* y_lo, cudaStream_t s);
 // tc_netvlad.cu
 int debug_gemm_tn(const float* A, const float* B, float* C, cudaStream_t s);
 int netvlad_tc_units(int B, int S);

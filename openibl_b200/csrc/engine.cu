@@ -2,6 +2,8 @@
 // arena and the re-laid-out weights; every entry point validates its arguments, enqueues
 // kernels on the caller's stream and returns a status code -- it never throws and never
 // synchronises, except for the *_host variants.
+#include <stdlib.h>
+
 #include <mutex>
 #include <new>
 #include <vector>
@@ -59,6 +61,7 @@ struct ibl_engine {
   uint64_t launches = 0;
   bool vgg_ready = false;
   ConvParams conv[13];
+  float* w0_oihw = nullptr;   // conv1_1 filters in the reference OIHW layout (tcgen05 conv1_1 builds its own operand)
   // borrowed NetVLAD / PCA parameters (owned by the caller's torch Parameters)
   const float* nv_w = nullptr;
   const float* nv_c = nullptr;
@@ -78,6 +81,8 @@ struct ibl_engine {
   DevBuf mrg_d, mrg_i;
   DevBuf ssq, nv_part, nv_asum, nvw_pl;  // fused NetVLAD: |x|^2 partials, unit partials, W planes [64,512]
   const float* nvw_pl_src = nullptr;
+  cudaStream_t copy_stream = nullptr;   // H2D staging of ibl_extract_host overlaps compute
+  cudaEvent_t copy_ev[2] = {nullptr, nullptr};
 };
 
 // conv5_3 output as bf16 hi/lo planes (fused-NetVLAD path)
@@ -135,7 +140,14 @@ int vgg_forward_impl(ibl_engine* e, const float* x, int N, int H, int W, float* 
   auto hi_of = [&](int b, size_t elems) { (void)elems; return e->act[b].as<__nv_bfloat16>(); };
   auto lo_of = [&](int b, size_t elems) { return e->act[b].as<__nv_bfloat16>() + elems; };
   size_t elems = (size_t)N * h * w * 64;
-  IBL_RET(launch_conv1_1(x, e->conv[0], N, h, w, true, nullptr, hi_of(0, elems), lo_of(0, elems), s));
+  {
+    static int simt1 = -1;   // IBL_CONV1_SIMT=1: keep conv1_1 on the CUDA cores (A/B experiments)
+    if (simt1 < 0) { const char* v = getenv("IBL_CONV1_SIMT"); simt1 = (v && atoi(v)) ? 1 : 0; }
+    if (simt1)
+      IBL_RET(launch_conv1_1(x, e->conv[0], N, h, w, true, nullptr, hi_of(0, elems), lo_of(0, elems), s));
+    else
+      IBL_RET(launch_conv1_1_tc(x, e->w0_oihw, e->conv[0].bias, N, h, w, hi_of(0, elems), lo_of(0, elems), s));
+  }
   e->launches++;
   for (int l = 1; l < 13; ++l) {
     const ConvLayer& L = kVgg16[l];
@@ -219,6 +231,8 @@ int ibl_engine_destroy(ibl_engine* e) {
     if (c.w_hi) cudaFree(c.w_hi);
     if (c.w_lo) cudaFree(c.w_lo);
   }
+  if (e->w0_oihw) cudaFree(e->w0_oihw);
+  if (e->copy_stream) { cudaStreamDestroy(e->copy_stream); cudaEventDestroy(e->copy_ev[0]); cudaEventDestroy(e->copy_ev[1]); }
   DevBuf* bufs[] = {&e->act[0], &e->act[1], &e->feat, &e->nv_assign, &e->nv_inv, &e->nv_raw, &e->vlad,
                     &e->pca_partial, &e->qn, &e->dbn, &e->dist_chunk, &e->cand_d, &e->cand_i,
                     &e->stage_in, &e->stage_out, &e->stage_out2, &e->q_pl, &e->db_pl, &e->v_pl, &e->pca_pl,
@@ -268,6 +282,10 @@ int ibl_engine_set_vgg16(ibl_engine* e, const float* const* w13, const float* co
     }
     IBL_RET(launch_repack_weights(w13[l], L.cout, L.cin, p, S(stream)));
     IBL_CUDA_OK(cudaMemcpyAsync(p.bias, b13[l], L.cout * sizeof(float), cudaMemcpyDeviceToDevice, S(stream)));
+    if (l == 0) {
+      if (!e->w0_oihw) IBL_CUDA_OK(cudaMalloc(&e->w0_oihw, nw * sizeof(float)));
+      IBL_CUDA_OK(cudaMemcpyAsync(e->w0_oihw, w13[0], nw * sizeof(float), cudaMemcpyDeviceToDevice, S(stream)));
+    }
     e->launches++;
   }
   e->vgg_ready = true;
@@ -354,7 +372,7 @@ int ibl_netvlad_forward(ibl_engine* e, const float* feat, int nhwc, int N, int C
     IBL_RET(launch_row_sqnorm(feat, N * S_, C, e->ssq.as<float>(), s));
     const int G = netvlad_tc_units(N, S_);
     IBL_RET(e->nv_part.ensure((size_t)N * G * 64 * 512 * sizeof(float)));
-    IBL_RET(e->nv_asum.ensure((size_t)N * G * 64 * sizeof(float)));
+    IBL_RET(e->nv_asum.ensure((size_t)N * (G + 1) * 64 * sizeof(float)));
     IBL_RET(launch_netvlad_tc(xh, xh + ne, N, S_, wh, wh + nw, e->ssq.as<float>(), 1, centroids,
                               normalize_input != 0, e->nv_part.as<float>(), e->nv_asum.as<float>(), vlad_raw,
                               vlad_norm, s));
@@ -460,7 +478,7 @@ int ibl_extract(ibl_engine* e, const float* x, int N, int H, int W, unsigned fla
       }
       const int G = netvlad_tc_units(nb, Sp);
       IBL_RET(e->nv_part.ensure((size_t)nb * G * 64 * 512 * sizeof(float)));
-      IBL_RET(e->nv_asum.ensure((size_t)nb * G * 64 * sizeof(float)));
+      IBL_RET(e->nv_asum.ensure((size_t)nb * (G + 1) * 64 * sizeof(float)));
       const size_t nw = (size_t)64 * 512;
       IBL_RET(launch_netvlad_tc(fp.hi, fp.lo, nb, Sp, e->nvw_pl.as<__nv_bfloat16>(), e->nvw_pl.as<__nv_bfloat16>() + nw,
                                 e->ssq.as<float>(), fp.ssq_parts, e->nv_c, true, e->nv_part.as<float>(),
@@ -492,9 +510,29 @@ int ibl_extract_host(ibl_engine* e, const float* x_host, int N, int H, int W, un
   IBL_RET(e->stage_in.ensure(in_bytes));
   IBL_RET(e->stage_out.ensure((size_t)N * out_dim * sizeof(float)));
   if (flags & IBL_OUT_POOL) IBL_RET(e->stage_out2.ensure((size_t)N * 512 * sizeof(float)));
-  IBL_CUDA_OK(cudaMemcpyAsync(e->stage_in.p, x_host, in_bytes, cudaMemcpyHostToDevice, S(stream)));
-  IBL_RET(ibl_extract(e, e->stage_in.as<float>(), N, H, W, flags, e->stage_out.as<float>(),
-                      (flags & IBL_OUT_POOL) ? e->stage_out2.as<float>() : nullptr, stream));
+  // Two half-batches: the H2D copy of the second half runs on the engine's copy stream while the
+  // first half is being computed (the reference serialises .cuda() and the forward, evaluators.py:24).
+  const int halves = N >= 16 ? 2 : 1;
+  if (!e->copy_stream) {
+    IBL_CUDA_OK(cudaStreamCreateWithFlags(&e->copy_stream, cudaStreamNonBlocking));
+    IBL_CUDA_OK(cudaEventCreateWithFlags(&e->copy_ev[0], cudaEventDisableTiming));
+    IBL_CUDA_OK(cudaEventCreateWithFlags(&e->copy_ev[1], cudaEventDisableTiming));
+  }
+  const size_t img_elems = (size_t)3 * H * W;
+  const int n_first = halves == 2 ? N / 2 : N;
+  for (int i = 0; i < halves; ++i) {
+    const int n0 = i == 0 ? 0 : n_first, nb = i == 0 ? n_first : N - n_first;
+    IBL_CUDA_OK(cudaMemcpyAsync(e->stage_in.as<float>() + n0 * img_elems, x_host + n0 * img_elems,
+                                nb * img_elems * sizeof(float), cudaMemcpyHostToDevice, e->copy_stream));
+    IBL_CUDA_OK(cudaEventRecord(e->copy_ev[i], e->copy_stream));
+  }
+  for (int i = 0; i < halves; ++i) {
+    const int n0 = i == 0 ? 0 : n_first, nb = i == 0 ? n_first : N - n_first;
+    IBL_CUDA_OK(cudaStreamWaitEvent(S(stream), e->copy_ev[i], 0));
+    IBL_RET(ibl_extract(e, e->stage_in.as<float>() + n0 * img_elems, nb, H, W, flags,
+                        e->stage_out.as<float>() + (size_t)n0 * out_dim,
+                        (flags & IBL_OUT_POOL) ? e->stage_out2.as<float>() + (size_t)n0 * 512 : nullptr, stream));
+  }
   IBL_CUDA_OK(cudaMemcpyAsync(out_host, e->stage_out.p, (size_t)N * out_dim * sizeof(float),
                               cudaMemcpyDeviceToHost, S(stream)));
   if ((flags & IBL_OUT_POOL) && pool_host)
@@ -778,7 +816,8 @@ int ibl_debug_time_layer(ibl_engine* e, int layer, const float* x, int N, int H,
   for (int r = -1; r < reps && rc == IBL_OK; ++r) {       // r = -1 is a warm-up launch
     if (r == 0) cudaEventRecord(e0, nullptr);
     if (layer == 0)
-      rc = launch_conv1_1(x, e->conv[0], N, H, W, true, nullptr, oh_, oh_ + out_e, nullptr);
+      rc = bn_override == 1 ? launch_conv1_1(x, e->conv[0], N, H, W, true, nullptr, oh_, oh_ + out_e, nullptr)
+                            : launch_conv1_1_tc(x, e->w0_oihw, e->conv[0].bias, N, H, W, oh_, oh_ + out_e, nullptr);
     else
       rc = launch_conv3x3_tc(ih, ih + in_e, e->conv[layer], N, H, W, L.cin, L.cout, L.relu, L.pool,
                              layer == 12 ? nullptr : oh_, layer == 12 ? nullptr : oh_ + out_e,

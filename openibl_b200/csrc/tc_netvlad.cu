@@ -198,6 +198,14 @@ netvlad_tc_kernel(const __grid_constant__ CUtensorMap tm_xhi, const __grid_const
       int stage = 0; uint32_t phase = 0;
       for (int unit = blockIdx.x; unit < n_units; unit += gridDim.x) {
         const int b = unit / a.G, g = unit - b * a.G;
+        // Pull every tile of this unit into L2 now: the ring below only keeps 3 stages in flight, which
+        // would expose one HBM round trip per stage; with the prefetch HBM streams in the background.
+        for (int t = g; t < a.T; t += a.G) {
+          for (int c = 0; c < 8; ++c) {
+            tma_prefetch_3d(&tm_xhi, c * 64, t * 128, b);
+            tma_prefetch_3d(&tm_xlo, c * 64, t * 128, b);
+          }
+        }
         for (int t = g; t < a.T; t += a.G) {
           const int p0 = t * 128;
           for (int c = 0; c < 8; ++c) {          // GEMM 1 stages: one 64-channel chunk + its W chunk
@@ -420,62 +428,57 @@ netvlad_tc_kernel(const __grid_constant__ CUtensorMap tm_xhi, const __grid_const
   if (warp == 1) { tc_fence_after(); tmem_dealloc(tmem_base, 512); }
 }
 
-// vlad[k,c] = sum_g part[b,g,k,c] - cent[k,c] * sum_g asum[b,g,k]; intra-normalise, flatten, L2
+// vlad[k,c] = sum_g part[b,g,k,c] - cent[k,c] * sum_g asum[b,g,k]; intra-normalise (netvlad.py:78).
+// grid (8, B): one warp per cluster row, 16 channels per lane held in registers.  Writes the raw VLAD
+// (if asked), the intra-normalised rows, and each row's squared norm for the global L2 pass.
 __global__ void __launch_bounds__(256)
-netvlad_finalize_kernel(const float* __restrict__ part, const float* __restrict__ asum_part, int G,
-                        const float* __restrict__ cent, float* __restrict__ vlad_raw /*nullable*/,
-                        float* __restrict__ vlad_norm /*nullable*/) {
-  __shared__ float row_inv[64], row_ss[64], asum[64];
-  __shared__ float ginv_s;
-  const long long b = blockIdx.x;
+netvlad_finalize_rows_kernel(const float* __restrict__ part, const float* __restrict__ asum_part, int G,
+                             const float* __restrict__ cent, float* __restrict__ vlad_raw /*nullable*/,
+                             float* __restrict__ vlad_norm /*nullable*/, float* __restrict__ row_ss /*[B][64]*/) {
+  const long long b = blockIdx.y;
   const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
-  if (threadIdx.x < 64) {
-    float s = 0.f;
-    for (int g = 0; g < G; ++g) s += asum_part[(b * G + g) * 64 + threadIdx.x];
-    asum[threadIdx.x] = s;
+  const int k = blockIdx.x * 8 + wid;
+  float asum = 0.f;
+  for (int g = 0; g < G; ++g) asum += __ldg(asum_part + (b * G + g) * 64 + k);
+  float v[16];
+  float ss = 0.f;
+#pragma unroll
+  for (int j = 0; j < 16; ++j) {
+    const int c = lane + 32 * j;
+    float acc = 0.f;
+    for (int g = 0; g < G; ++g) acc += __ldg(part + ((b * G + g) * 64 + k) * 512 + c);
+    acc -= __ldg(cent + k * 512 + c) * asum;
+    v[j] = acc;
+    ss = fmaf(acc, acc, ss);
   }
-  __syncthreads();
-  // each warp owns 8 cluster rows; a lane holds 16 channels of the row in registers
-  for (int k = wid * 8; k < wid * 8 + 8; ++k) {
-    float v[16];
-    float ss = 0.f;
 #pragma unroll
-    for (int j = 0; j < 16; ++j) {
-      const int c = lane + 32 * j;
-      float acc = 0.f;
-      for (int g = 0; g < G; ++g) acc += part[((b * G + g) * 64 + k) * 512 + c];
-      acc -= __ldg(cent + k * 512 + c) * asum[k];
-      v[j] = acc;
-      ss = fmaf(acc, acc, ss);
-    }
+  for (int o = 16; o > 0; o >>= 1) ss += __shfl_xor_sync(0xffffffffu, ss, o);
+  const float inv = 1.f / fmaxf(sqrtf(ss), 1e-12f);
+  float s2 = 0.f;
 #pragma unroll
-    for (int o = 16; o > 0; o >>= 1) ss += __shfl_xor_sync(0xffffffffu, ss, o);
-    const float inv = 1.f / fmaxf(sqrtf(ss), 1e-12f);
-    float s2 = 0.f;
-#pragma unroll
-    for (int j = 0; j < 16; ++j) {
-      const int c = lane + 32 * j;
-      if (vlad_raw) vlad_raw[(b * 64 + k) * 512 + c] = v[j];
-      const float w = v[j] * inv;
-      s2 = fmaf(w, w, s2);
-      if (vlad_norm) vlad_norm[(b * 64 + k) * 512 + c] = w;     // scaled by the global norm below
-    }
-#pragma unroll
-    for (int o = 16; o > 0; o >>= 1) s2 += __shfl_xor_sync(0xffffffffu, s2, o);
-    if (lane == 0) { row_inv[k] = inv; row_ss[k] = s2; }
+  for (int j = 0; j < 16; ++j) {
+    const int c = lane + 32 * j;
+    if (vlad_raw) vlad_raw[(b * 64 + k) * 512 + c] = v[j];
+    const float w = v[j] * inv;
+    s2 = fmaf(w, w, s2);
+    if (vlad_norm) vlad_norm[(b * 64 + k) * 512 + c] = w;
   }
-  __syncthreads();
-  if (!vlad_norm) return;
-  if (threadIdx.x < 32) {
-    float tot = row_ss[lane] + row_ss[lane + 32];
 #pragma unroll
-    for (int o = 16; o > 0; o >>= 1) tot += __shfl_xor_sync(0xffffffffu, tot, o);
-    if (lane == 0) ginv_s = 1.f / fmaxf(sqrtf(tot), 1e-12f);
-  }
-  __syncthreads();
-  const float ginv = ginv_s;
-  float4* o = reinterpret_cast<float4*>(vlad_norm + b * 64 * 512);
-  for (int e = threadIdx.x; e < 64 * 512 / 4; e += 256) {
+  for (int o = 16; o > 0; o >>= 1) s2 += __shfl_xor_sync(0xffffffffu, s2, o);
+  if (lane == 0) row_ss[b * 64 + k] = s2;
+}
+
+// global L2 over the flattened 64x512 descriptor (netvlad.py:79-80): grid (8, B), in place
+__global__ void __launch_bounds__(256)
+netvlad_finalize_l2_kernel(float* __restrict__ vlad_norm, const float* __restrict__ row_ss) {
+  const long long b = blockIdx.y;
+  const int lane = threadIdx.x & 31;
+  float tot = __ldg(row_ss + b * 64 + lane) + __ldg(row_ss + b * 64 + lane + 32);
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) tot += __shfl_xor_sync(0xffffffffu, tot, o);
+  const float ginv = 1.f / fmaxf(sqrtf(tot), 1e-12f);
+  float4* o = reinterpret_cast<float4*>(vlad_norm + (b * 64 + blockIdx.x * 8) * 512);
+  for (int e = threadIdx.x; e < 8 * 512 / 4; e += 256) {
     float4 w = o[e];
     w.x *= ginv; w.y *= ginv; w.z *= ginv; w.w *= ginv;
     o[e] = w;
@@ -530,8 +533,13 @@ int launch_netvlad_tc(const __nv_bfloat16* x_hi, const __nv_bfloat16* x_lo, int 
   const int units = B * a.G;
   netvlad_tc_kernel<<<units < sms ? units : sms, 192, smem, s>>>(mx_hi, mx_lo, mw_hi, mw_lo, a);
   IBL_CUDA_OK(cudaGetLastError());
-  netvlad_finalize_kernel<<<B, 256, 0, s>>>(part, asum_part, a.G, cent, vlad_raw, vlad_norm);
+  float* row_ss = asum_part + (size_t)units * 64;   // caller sizes asum_part as [units + B][64]
+  netvlad_finalize_rows_kernel<<<dim3(8, B), 256, 0, s>>>(part, asum_part, a.G, cent, vlad_raw, vlad_norm, row_ss);
   IBL_CUDA_OK(cudaGetLastError());
+  if (vlad_norm) {
+    netvlad_finalize_l2_kernel<<<dim3(8, B), 256, 0, s>>>(vlad_norm, row_ss);
+    IBL_CUDA_OK(cudaGetLastError());
+  }
   return IBL_OK;
 }
 

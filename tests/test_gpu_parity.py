@@ -119,7 +119,7 @@ def test_small_96x128_every_stage_vs_reference(eng):
         assert rel_l2(nrm.cpu(), g["vlad"]) < DESC_TOL / 4, name
         vlad, pool2 = eng.extract(x, pca=False, want_pool=True)
         assert rel_l2(vlad.cpu(), g["vlad"]) < DESC_TOL / 4, name
-        assert torch.equal(pool2, pool)
+        assert rel_l2(pool2.cpu(), pool.cpu()) < 2e-5   # fused path pools the bf16 hi+lo planes
         desc, _ = eng.extract(x, pca=True)
         assert rel_l2(desc.cpu(), g["desc"]) < DESC_TOL, name
 

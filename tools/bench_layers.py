@@ -25,7 +25,7 @@ print(f"{'layer':8s} {'HxW':>9s} {'Cin':>4s} {'Cout':>4s} {'BN':>4s} {'ms':>8s} 
 for li, (hh, ww, cin, cout) in enumerate(shapes):
     if li == 0:
         x = torch.randn(B, 3, hh, ww, device="cuda")
-        bns = [0]
+        bns = [0, 1]   # 0 = tcgen05 conv1_1, 1 = CUDA-core conv1_1
     else:
         x = torch.randn(B, hh, ww, cin, device="cuda").relu_()
         bns = [b for b in (64, 128, 256) if cout % b == 0]
