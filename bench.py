@@ -54,7 +54,7 @@ class ClockSampler:
         try:
             self.proc = subprocess.Popen(
                 ["nvidia-smi", "-i", str(self.index), f"--query-gpu={self.Q}", "--format=csv,noheader,nounits",
-                 "-lms", "100"], stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+                 "-lms", "50"], stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
             self.t = threading.Thread(target=self._read, daemon=True)
             self.t.start()
         except Exception:
@@ -111,15 +111,22 @@ def run_reference(args):
         return
     cores = os.cpu_count()
     torch.set_num_threads(cores)
-    per_step = 2                                   # bounded sample: 2 images of the batch-32 workload
-    for _ in range(min(args.warmup, 1)):
-        cpu_reference_images_per_sec(1)
-    t0 = time.perf_counter()
-    n = 0
-    for _ in range(args.steps):
-        cpu_reference_images_per_sec(per_step)
-        n += per_step
-    dt = time.perf_counter() - t0
+    # bounded sample of the batch-32 workload: <= 4 images per step and <= ~64 images in total,
+    # so the whole run stays within a few minutes at ~0.5-1 image/s of CPU throughput
+    per_step = max(1, min(4, 64 // max(args.steps, 1)))
+    from oracle import ibl_oracle as O
+    from openibl_b200 import synth
+    sd = synth.make_state_dict(seed=0, with_pca=True)          # parameters and inputs are built outside
+    x = synth.make_images(seed=1, batch=per_step)              # the timed region, as on the GPU arm
+    with torch.no_grad():
+        for _ in range(min(args.warmup, 1)):
+            O.extract_descriptor(x[:1], sd)
+        t0 = time.perf_counter()
+        n = 0
+        for _ in range(args.steps):
+            O.extract_descriptor(x, sd)
+            n += per_step
+        dt = time.perf_counter() - t0
     val = n / dt
     pps, _ = cpu_reference_pairs_per_sec(400, NDB)
     line = {
@@ -141,7 +148,7 @@ def run_reference(args):
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
-    ap.add_argument("--steps", type=int, default=10)
+    ap.add_argument("--steps", type=int, default=30)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--conv-mode", default="tc", choices=["tc", "simt"])

@@ -418,8 +418,14 @@ rescore_sort_kernel(const float* __restrict__ q, const float* __restrict__ qn,
   __shared__ unsigned long long keys[128];
   const long long row = blockIdx.x;
   const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
-  for (int i = threadIdx.x * 4; i < d; i += 128 * 4)
-    *reinterpret_cast<float4*>(qs + i) = __ldg(reinterpret_cast<const float4*>(q + row * d + i));
+  // the query row is staged in shared memory when it fits (d <= 16384, e.g. the 4096-d PCA
+  // descriptors); the 32768-d raw VLAD is read through L1 instead
+  const bool staged = d <= 16384;
+  if (staged) {
+    for (int i = threadIdx.x * 4; i < d; i += 128 * 4)
+      *reinterpret_cast<float4*>(qs + i) = __ldg(reinterpret_cast<const float4*>(q + row * d + i));
+  }
+  const float* qrow = staged ? qs : (q + row * d);
   __syncthreads();
   const float an = __ldg(qn + row);
   for (int c = wid; c < 128; c += 4) {
@@ -430,7 +436,7 @@ rescore_sort_kernel(const float* __restrict__ q, const float* __restrict__ qn,
         const float* dp = db + ci * d;
         float acc = 0.f;
         for (int i = lane * 4; i < d; i += 128) {
-          const float4 a = *reinterpret_cast<const float4*>(qs + i);
+          const float4 a = *reinterpret_cast<const float4*>(qrow + i);
           const float4 b = __ldg(reinterpret_cast<const float4*>(dp + i));
           acc = fmaf(a.x, b.x, acc); acc = fmaf(a.y, b.y, acc);
           acc = fmaf(a.z, b.z, acc); acc = fmaf(a.w, b.w, acc);
@@ -475,14 +481,14 @@ int launch_rescore_sort(const float* q, const float* qn, int m, const float* db,
                         const long long* cand_i, int kc, int k_out, long long idx_base, float* out_dist,
                         long long* out_idx, cudaStream_t s) {
   IBL_REQUIRE(kc >= 1 && kc <= 128 && k_out >= 1 && k_out <= 128, "rescore: 1 <= k <= 128");
-  IBL_REQUIRE(d % 4 == 0 && d * 4 <= 64 * 1024, "rescore: dim must be a multiple of 4 and <= 16384");
+  IBL_REQUIRE(d % 4 == 0, "rescore: dim must be a multiple of 4");
   static bool attr_done = false;
   if (!attr_done) {
     IBL_CUDA_OK(cudaFuncSetAttribute(rescore_sort_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 64 * 1024));
     attr_done = true;
   }
   if (m == 0) return IBL_OK;
-  rescore_sort_kernel<<<m, 128, d * sizeof(float), s>>>(q, qn, db, dbn, d, cand_i, kc, k_out, idx_base,
+  rescore_sort_kernel<<<m, 128, d <= 16384 ? d * sizeof(float) : 16, s>>>(q, qn, db, dbn, d, cand_i, kc, k_out, idx_base,
                                                        out_dist, out_idx);
   IBL_CUDA_OK(cudaGetLastError());
   return IBL_OK;

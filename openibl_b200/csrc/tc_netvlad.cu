@@ -3,6 +3,8 @@
 // a TMA box [rows = k][64 contiguous elements] produces.  This is what the second NetVLAD contraction
 // needs: vlad[c,k] = sum_s x^[s,c] a[s,k] reads the same [pixel][channel] tile the first contraction
 // (logits = x^ W^T, K-major) already staged, so the feature map is read from HBM once.
+#include <stdlib.h>
+
 #include "common.cuh"
 #include "tc_common.cuh"
 
@@ -150,9 +152,20 @@ struct NvTcArgs {
   int normalize_input;
   float* part;                    // [B*G][64][512]   partial V^T (k-major rows, c contiguous)
   float* asum_part;               // [B*G][64]
+  unsigned long long* dbg;        // optional [gridDim][32] globaltimer stamps (IBL_NV_DEBUG=1)
 };
 
 constexpr int NV_STAGE = 65536, NV_NSTAGE = 3, NV_SLOT = 16384;
+
+__device__ __forceinline__ unsigned long long nv_now() {
+  unsigned long long t;
+  asm volatile("mov.u64 %0, %globaltimer;" : "=l"(t));
+  return t;
+}
+#define NV_STAMP(slot)                                                                    \
+  do {                                                                                    \
+    if (a.dbg && q == 0 && lane == 0 && (slot) < 32) a.dbg[blockIdx.x * 32 + (slot)] = nv_now(); \
+  } while (0)
 
 __global__ void __launch_bounds__(192, 1)
 netvlad_tc_kernel(const __grid_constant__ CUtensorMap tm_xhi, const __grid_constant__ CUtensorMap tm_xlo,
@@ -200,12 +213,8 @@ netvlad_tc_kernel(const __grid_constant__ CUtensorMap tm_xhi, const __grid_const
         const int b = unit / a.G, g = unit - b * a.G;
         // Pull every tile of this unit into L2 now: the ring below only keeps 3 stages in flight, which
         // would expose one HBM round trip per stage; with the prefetch HBM streams in the background.
-        for (int t = g; t < a.T; t += a.G) {
-          for (int c = 0; c < 8; ++c) {
-            tma_prefetch_3d(&tm_xhi, c * 64, t * 128, b);
-            tma_prefetch_3d(&tm_xlo, c * 64, t * 128, b);
-          }
-        }
+        // The unit's first tile is loaded by the ring itself; later tiles are prefetched right behind
+        // its first three stages (see below), so they do not delay it.
         for (int t = g; t < a.T; t += a.G) {
           const int p0 = t * 128;
           for (int c = 0; c < 8; ++c) {          // GEMM 1 stages: one 64-channel chunk + its W chunk
@@ -217,6 +226,13 @@ netvlad_tc_kernel(const __grid_constant__ CUtensorMap tm_xhi, const __grid_const
             tma_load_2d(st + 2 * NV_SLOT, &tm_whi, &full_bar[stage], c * 64, 0);
             tma_load_2d(st + 2 * NV_SLOT + 8192, &tm_wlo, &full_bar[stage], c * 64, 0);
             if (++stage == NV_NSTAGE) { stage = 0; phase ^= 1; }
+            if (t == g && c == 2) {
+              for (int t2 = g + a.G; t2 < a.T; t2 += a.G)
+                for (int c2 = 0; c2 < 8; ++c2) {
+                  tma_prefetch_3d(&tm_xhi, c2 * 64, t2 * 128, b);
+                  tma_prefetch_3d(&tm_xlo, c2 * 64, t2 * 128, b);
+                }
+            }
           }
           for (int cb = 0; cb < 4; ++cb) {       // GEMM 2 stages: one 128-channel block (L2 hits)
             mbar_wait(&empty_bar[stage], phase ^ 1);
@@ -300,6 +316,8 @@ netvlad_tc_kernel(const __grid_constant__ CUtensorMap tm_xhi, const __grid_const
     for (int unit = blockIdx.x; unit < n_units; unit += gridDim.x, ++u) {
       const int b = unit / a.G, g = unit - b * a.G;
       float as0 = 0.f, as1 = 0.f;                // sum_s a[s,k] for k = 2*lane, 2*lane+1 (this warp's rows)
+      int dslot = 1;
+      NV_STAMP(0);
       for (int t = g; t < a.T; t += a.G, ++it) {
         const int s = t * 128 + s_loc;
         const bool valid = s < a.S;
@@ -310,6 +328,7 @@ netvlad_tc_kernel(const __grid_constant__ CUtensorMap tm_xhi, const __grid_const
           inv = 1.f / fmaxf(sqrtf(ss), 1e-12f);
         }
         mbar_wait(z_full, it & 1);
+        NV_STAMP(dslot); ++dslot;                  // logits of this tile are ready
         tc_fence_after();
         float z[64];
         {
@@ -355,6 +374,7 @@ netvlad_tc_kernel(const __grid_constant__ CUtensorMap tm_xhi, const __grid_const
         tc_fence_before();
         __syncwarp();
         if (lane == 0) mbar_arrive(a_full);
+        NV_STAMP(dslot); ++dslot;                  // a' published
         // column sums of a over this warp's 32 rows: butterfly, lane L ends with columns 2L, 2L+1
         {
           float w32[32];
@@ -398,6 +418,7 @@ netvlad_tc_kernel(const __grid_constant__ CUtensorMap tm_xhi, const __grid_const
       asum_sm[q * 64 + 2 * lane] = as0;
       asum_sm[q * 64 + 2 * lane + 1] = as1;
       mbar_wait(d_full, u & 1);
+      NV_STAMP(dslot); ++dslot;                    // all MMAs of the unit retired
       tc_fence_after();
       float* po = a.part + (long long)unit * 64 * 512;
       for (int cb = 0; cb < 4; ++cb) {
@@ -421,6 +442,7 @@ netvlad_tc_kernel(const __grid_constant__ CUtensorMap tm_xhi, const __grid_const
       }
       asm volatile("bar.sync 1, 128;" ::: "memory");
       if (lane == 0) mbar_arrive(d_empty);
+      NV_STAMP(dslot); ++dslot;                    // partial written
     }
   }
   tc_fence_before();
@@ -521,6 +543,12 @@ int launch_netvlad_tc(const __nv_bfloat16* x_hi, const __nv_bfloat16* x_lo, int 
   a.B = B; a.S = S; a.T = cdiv(S, 128); a.G = netvlad_tc_units(B, S);
   a.ssq = ssq; a.ssq_parts = ssq_parts; a.normalize_input = normalize_input ? 1 : 0;
   a.part = part; a.asum_part = asum_part;
+  static unsigned long long* dbg_dev = nullptr;
+  static int dbg_on = -1;
+  if (dbg_on < 0) { const char* v = getenv("IBL_NV_DEBUG"); dbg_on = (v && atoi(v)) ? 1 : 0; }
+  if (dbg_on && !dbg_dev) { cudaMalloc(&dbg_dev, 148 * 32 * 8); }
+  if (dbg_on) cudaMemsetAsync(dbg_dev, 0, 148 * 32 * 8, s);
+  a.dbg = dbg_on ? dbg_dev : nullptr;
   const int smem = NV_NSTAGE * NV_STAGE + 2 * NV_SLOT + 1024 + 128 + 4 * 64 * 4;
   static bool attr_done = false;
   if (!attr_done) {
@@ -533,6 +561,18 @@ int launch_netvlad_tc(const __nv_bfloat16* x_hi, const __nv_bfloat16* x_lo, int 
   const int units = B * a.G;
   netvlad_tc_kernel<<<units < sms ? units : sms, 192, smem, s>>>(mx_hi, mx_lo, mw_hi, mw_lo, a);
   IBL_CUDA_OK(cudaGetLastError());
+  if (dbg_on) {   // print phase stamps of a few CTAs (ns relative to the earliest stamp)
+    cudaStreamSynchronize(s);
+    static unsigned long long h[148 * 32];
+    cudaMemcpy(h, dbg_dev, sizeof(h), cudaMemcpyDeviceToHost);
+    unsigned long long t0 = ~0ull;
+    for (int i = 0; i < 148 * 32; ++i) if (h[i] && h[i] < t0) t0 = h[i];
+    for (int c : {0, 1, 60, 127}) {
+      fprintf(stderr, "[nv-debug] cta %3d:", c);
+      for (int j = 0; j < 12; ++j) fprintf(stderr, " %6lld", h[c * 32 + j] ? (long long)(h[c * 32 + j] - t0) : -1ll);
+      fprintf(stderr, "\n");
+    }
+  }
   float* row_ss = asum_part + (size_t)units * 64;   // caller sizes asum_part as [units + B][64]
   netvlad_finalize_rows_kernel<<<dim3(8, B), 256, 0, s>>>(part, asum_part, a.G, cent, vlad_raw, vlad_norm, row_ss);
   IBL_CUDA_OK(cudaGetLastError());

@@ -159,6 +159,26 @@ def test_hub_480x640_config_vs_reference(eng):
         assert rel_l2(desc.cpu(), g["desc"]) < DESC_TOL, name
 
 
+def test_sharp_netvlad_full_chain_vs_oracle(eng, O):
+    """Random-init NetVLAD parameters make a weak test (descriptors are dominated by the centroid term and
+    differ by ~1e-6 between images).  With _init_params-style parameters (unit-norm centroids,
+    alpha ~ 280) the descriptor depends sharply on the feature map; this is the realistic case and the one
+    where the bf16x3 error is largest (measured 7e-5).  Tolerance: the north-star 1e-4."""
+    sd = synth.make_state_dict(seed=11, sharp=True, with_pca=False, bias_scale=0.02)
+    _bind(eng, sd)
+    x = synth.make_images(seed=12, batch=6, height=64, width=96)
+    with torch.no_grad():
+        _, want = O.embednet_forward(x, sd)
+    for name, mode, _ in _modes():
+        eng.conv_mode = mode
+        got, _ = eng.extract(x.cuda(), pca=False)
+        per_image = ((got.cpu().double() - want.double()).norm(dim=1) / want.double().norm(dim=1)).max().item()
+        assert per_image < DESC_TOL, (name, per_image)
+    # and the images really are distinguishable: pairwise distances are O(1e-2), not O(1e-6)
+    d = O.self_distance(want)
+    assert float(d[~torch.eye(6, dtype=torch.bool)].min()) > 1e-3
+
+
 def test_models_api_drop_in(eng):
     """The nn.Module mirror (what examples/test.py builds, :58-70) gives the golden outputs."""
     from ibl import models
@@ -317,6 +337,18 @@ def test_topk_edge_cases(eng, O):
         _topk_edge_cases(eng, O, q, db, qd, dbd, d)
 
 
+def test_topk_raw_vlad_dim_32768(eng, O):
+    """--vlad without --reduction ranks the 32768-d descriptors directly (examples/test.py:127-131)."""
+    q, db, _ = synth.make_gallery(n_db=300, n_q=9, dim=32768, sigma=0.02)
+    d = O.pairwise_distance(q, db).numpy()
+    wd, wi = O.topk_from_distmat(d, 10)
+    for name, mode, _ in GEMM_MODES:
+        eng.set_gemm_mode(mode)
+        dk, ik = eng.l2dist_topk(q.cuda(), db.cuda(), 10)
+        assert np.array_equal(ik.cpu().numpy(), wi), name
+        assert np.allclose(dk.cpu().numpy(), wd, atol=2e-5), name
+
+
 def _topk_edge_cases(eng, O, q, db, qd, dbd, d):
     # k = 1, k = 12/13 (register top-16 vs dense path), k = 128, padded shard, idx_base, duplicates
     for k in (1, 12, 13, 128):
@@ -368,6 +400,28 @@ def test_retrieval_pitts30k_shape_properties(eng):
     gl = [np.array([int(t)]) for t in gt[sel.cpu()]]
     assert np.array_equal(recalls_from_topk(ik[sel].cpu().numpy(), gl, gallery),
                           recalls_from_topk(wi.cpu().numpy(), gl, gallery))
+
+
+def test_retrieval_pitts250k_shard_shape(eng):
+    """configs[3] per-GPU shape: 6.8k queries x one 31,250-row shard (250k / 8) x 4096, with the
+    DistributedSliceSampler padding masked out (n_valid < n) and a non-zero index base.  Checked against
+    an exact fp64 ranking of a query subset and by merging two half-shards."""
+    n, n_valid, base = 31250, 31000, 3 * 31250
+    q, db, gt = synth.make_gallery(n, 6800, 4096, seed_db=7, seed_q=8)
+    qd, dbd = q.cuda(), db.cuda()
+    dk, ik = eng.l2dist_topk(qd, dbd, 10, idx_base=base, n_valid=n_valid)
+    assert bool((dk[:, 1:] >= dk[:, :-1]).all())
+    assert int(ik.min()) >= base and int(ik.max()) < base + n_valid
+    sel = torch.arange(0, 6800, 211, device="cuda")
+    exact = 2 - 2 * (qd[sel].double() @ dbd[:n_valid].double().t())
+    wd, wi = exact.topk(10, largest=False)
+    assert float((dk[sel].double() - wd).abs().max()) < 5e-6
+    assert float((ik[sel] == wi + base).float().mean()) > 0.99
+    h = n_valid // 2
+    a = eng.l2dist_topk(qd, dbd[:h].contiguous(), 10, idx_base=base)
+    b = eng.l2dist_topk(qd, dbd[h:n_valid].contiguous(), 10, idx_base=base + h)
+    md, mi = eng.topk_merge(torch.stack([a[0], b[0]]), torch.stack([a[1], b[1]]), 10)
+    assert float((mi == ik).float().mean()) > 0.9995 and float((md - dk).abs().max()) < 5e-6
 
 
 # ---------------------------------------------------------------------------------------------
