@@ -519,7 +519,8 @@ int ibl_extract_host(ibl_engine* e, const float* x_host, int N, int H, int W, un
     IBL_CUDA_OK(cudaEventCreateWithFlags(&e->copy_ev[1], cudaEventDisableTiming));
   }
   const size_t img_elems = (size_t)3 * H * W;
-  const int n_first = halves == 2 ? N / 2 : N;
+  // uneven split: only the first (small) part's copy is exposed; the rest streams in behind its compute
+  const int n_first = halves == 2 ? (N / 4 > 0 ? N / 4 : 1) : N;
   for (int i = 0; i < halves; ++i) {
     const int n0 = i == 0 ? 0 : n_first, nb = i == 0 ? n_first : N - n_first;
     IBL_CUDA_OK(cudaMemcpyAsync(e->stage_in.as<float>() + n0 * img_elems, x_host + n0 * img_elems,

@@ -12,6 +12,8 @@
 //
 // Work item = (row tile of 128, a run of column tiles, a run of K chunks); items are dealt
 // round-robin to a persistent grid.  Warp roles as in tc_conv.cu.
+#include <stdlib.h>
+
 #include "common.cuh"
 #include "tc_common.cuh"
 
@@ -314,19 +316,28 @@ static int pick_runs(int m_tiles, int n_tiles, int min_tiles_per_run) {
 }
 
 // Distance + running top-16 per (query, column run): cand_* [runs][M][16]; returns runs.
+// N tile of the distance kernel.  The kernel is bound by L2->SM operand traffic (profiles/r01_dist_tc.md);
+// a 256-column tile (IBL_DIST_BN=256) halves the re-read of the query tile but only fits 2 pipeline
+// stages, and measured the same 1.91 ms as 128 columns x 3 stages on 6.8k x 10k x 4096 -- 128 stays default.
+static int dist_bn() {
+  static int bn = 0;
+  if (!bn) { const char* v = getenv("IBL_DIST_BN"); bn = (v && atoi(v) == 256) ? 256 : 128; }
+  return bn;
+}
+
 int launch_dist_top16_tc(const __nv_bfloat16* q_hi, const __nv_bfloat16* q_lo, const float* qn, int m,
                          const __nv_bfloat16* d_hi, const __nv_bfloat16* d_lo, const float* dn, int n,
                          int n_valid, int K, float* cand_d, long long* cand_i, int max_runs, int* runs_out,
                          cudaStream_t s) {
   IBL_REQUIRE(K % 64 == 0, "tcgen05 distance needs dim % 64 == 0");
-  constexpr int BN = 128;
+  const int BN = dist_bn();
   CUtensorMap maps[4];
   IBL_RET(make_plane_maps(maps, q_hi, q_lo, m, d_hi, d_lo, n, K, BN));
   GemmTcArgs g{};
   g.M = m; g.N = n; g.K = K;
   g.n_tiles = cdiv(n_valid > 0 ? n_valid : 1, BN);
   const int m_tiles = cdiv(m, GT_BM);
-  int runs = pick_runs(m_tiles, g.n_tiles, 2);
+  int runs = pick_runs(m_tiles, g.n_tiles, BN == 256 ? 1 : 2);
   if (runs > max_runs) runs = max_runs;
   g.nt_per_item = cdiv(g.n_tiles, runs);
   g.items_per_mtile = cdiv(g.n_tiles, g.nt_per_item);
@@ -336,11 +347,13 @@ int launch_dist_top16_tc(const __nv_bfloat16* q_hi, const __nv_bfloat16* q_lo, c
   g.an = qn; g.bn = dn;
   g.cand_d = cand_d; g.cand_i = cand_i;
   *runs_out = g.items_per_mtile;
-  return launch_gemm_variant<BN, 3, EPI_TOP16>(maps, g, s);
+  if (BN == 256) return launch_gemm_variant<256, 2, EPI_TOP16>(maps, g, s);
+  return launch_gemm_variant<128, 3, EPI_TOP16>(maps, g, s);
 }
 
 int dist_top16_max_runs(int m, int n_valid) {
-  return pick_runs(cdiv(m, GT_BM), cdiv(n_valid > 0 ? n_valid : 1, 128), 2);
+  const int BN = dist_bn();
+  return pick_runs(cdiv(m, GT_BM), cdiv(n_valid > 0 ? n_valid : 1, BN), BN == 256 ? 1 : 2);
 }
 
 int launch_dist_dense_tc(const __nv_bfloat16* q_hi, const __nv_bfloat16* q_lo, const float* qn, int m,
