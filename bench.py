@@ -229,13 +229,36 @@ def main():
     bb_ms = b0.elapsed_time(b1) / nb
     pk = peaks()
     ach = GFLOP_PER_IMAGE_BACKBONE * BATCH / bb_ms          # GFLOP/ms == TFLOP/s
-    roofline = {"bound": "tensor", "kernel": "vgg16 backbone: conv1_1 (CUDA cores) + 12 tcgen05 implicit-GEMM convs",
-                "achieved": ach, "peak": pk["bf16_tflops_sustained"], "unit": "TFLOP/s",
-                "frac": ach / pk["bf16_tflops_sustained"], "traffic": None,
+    # the dominant kernel itself: conv3x3_tc_kernel, timed launch by launch (12 layers, CUDA events inside
+    # the library on the launching stream, 3 repetitions each after a warm-up launch)
+    import ctypes
+    shapes, hh, ww = [], H, W
+    for item in synth.VGG16_PLAN:
+        if item == "P":
+            hh, ww = hh // 2, ww // 2
+        else:
+            shapes.append((hh, ww, item[1], item[2]))
+    conv_ms, conv_gflop = 0.0, 0.0
+    for li, (lh, lw, cin, cout) in enumerate(shapes):
+        if li == 0:
+            continue
+        xin = torch.randn(BATCH, lh, lw, cin, device=dev).relu_()
+        msl = ctypes.c_float()
+        check(eng.lib.ibl_debug_time_layer(eng.h, li, _ptr(xin), BATCH, lh, lw, 0, 3, ctypes.byref(msl)), "time_layer")
+        conv_ms += msl.value
+        conv_gflop += 2.0 * BATCH * lh * lw * 9 * cin * cout / 1e9
+        del xin
+    ach_k = conv_gflop / conv_ms
+    roofline = {"bound": "tensor", "kernel": "conv3x3_tc_kernel (12 launches: conv1_2..conv5_3, tcgen05 implicit GEMM, bf16x3)",
+                "achieved": ach_k, "peak": pk["bf16_tflops_sustained"], "unit": "TFLOP/s",
+                "frac": ach_k / pk["bf16_tflops_sustained"],
+                "traffic": 601.3e6, "traffic_note": "ncu dram read+write of one representative launch (conv3_2, 256->256 @120x160, "
+                "B=32: 329 MB + 272 MB vs 315 MB of activations in/out + 9 MB weights), profiles/r01_conv256_tc.md",
                 "peak_source": pk["src"] + " bf16 sustained (cuBLAS)",
-                "note": "algorithmic fp32-grade FLOPs; the bf16x3 split issues 3 MMA passes per product, "
-                        "so tensor-pipe work is 3x the algorithmic figure",
-                "ms_per_launch_group": bb_ms, "mma_issue_frac": 3 * ach / pk["bf16_tflops_sustained"]}
+                "note": "achieved = algorithmic fp32-grade FLOPs / sum of the 12 launch durations; the bf16x3 split issues "
+                        "3 MMA passes per product, so the tensor pipe executes 3x the algorithmic figure (mma_issue_frac)",
+                "ms_per_launch_group": conv_ms, "mma_issue_frac": 3 * ach_k / pk["bf16_tflops_sustained"],
+                "backbone_13_launches": {"ms": bb_ms, "achieved": ach, "frac": ach / pk["bf16_tflops_sustained"]}}
 
     # ---- end to end through host buffers -----------------------------------------------------
     for i in range(2):

@@ -126,6 +126,9 @@ int ibl_extract_host(ibl_engine* e, const float* x_nchw_host, int N, int H, int 
                      unsigned flags, float* out_host, float* pool_host, void* stream);
 
 /* ---- stage (iii-b): distance + ranking ------------------------------------- */
+/* pairwise_distance(features) with query = gallery = None (evaluators.py:106-114):
+ * out[i,j] = 2|x_i|^2 - 2 x_i.x_j, x [n,d], out [n,n]. */
+int ibl_l2dist_self(ibl_engine* e, const float* x, int n, int d, float* out, void* stream);
 /* pairwise_distance (evaluators.py:127-129): out[i,j] = |q_i|^2 + |db_j|^2 - 2 q_i.db_j,
  * q [m,d], db [n,d], out [m,n].  Kept for the callers that need the dense matrix
  * (netvlad_img.py:78). */

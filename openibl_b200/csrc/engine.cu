@@ -569,6 +569,32 @@ int ibl_l2dist_dense(ibl_engine* e, const float* q, int m, const float* db, int 
   return IBL_OK;
 }
 
+// pairwise_distance(features) with query=gallery=None (evaluators.py:106-114):
+// out[i,j] = 2|x_i|^2 - 2 x_i.x_j  (the reference broadcasts 2|x_i|^2 over the whole row)
+int ibl_l2dist_self(ibl_engine* e, const float* x, int n, int d, float* out, void* stream) {
+  IBL_REQUIRE(e && x && out, "null argument");
+  IBL_REQUIRE(n >= 1 && d >= 4 && d % 4 == 0, "bad shape");
+  DeviceGuard g(e->device);
+  cudaStream_t s = S(stream);
+  IBL_RET(e->qn.ensure((size_t)n * sizeof(float)));
+  IBL_RET(e->dbn.ensure((size_t)n * sizeof(float)));
+  IBL_RET(launch_row_sqnorm(x, n, d, e->qn.as<float>(), s));
+  IBL_RET(launch_scale(e->qn.as<float>(), 2.f, n, e->qn.as<float>(), s));   // row term 2|x_i|^2
+  IBL_CUDA_OK(cudaMemsetAsync(e->dbn.p, 0, (size_t)n * sizeof(float), s));   // no column term
+  if (e->gemm_mode == IBL_CONV_TC_BF16X3 && d % 64 == 0) {
+    const size_t ne = (size_t)n * d;
+    IBL_RET(e->q_pl.ensure(ne * 4));
+    __nv_bfloat16* xh = e->q_pl.as<__nv_bfloat16>();
+    IBL_RET(launch_f32_to_planes(x, ne, xh, xh + ne, s));
+    IBL_RET(launch_dist_dense_tc(xh, xh + ne, e->qn.as<float>(), n, xh, xh + ne, e->dbn.as<float>(), n, d, out, n, s));
+    e->launches += 4;
+    return IBL_OK;
+  }
+  IBL_RET(launch_l2dist_dense(x, e->qn.as<float>(), n, x, e->dbn.as<float>(), n, d, out, n, s));
+  e->launches += 3;
+  return IBL_OK;
+}
+
 int ibl_l2dist_topk(ibl_engine* e, const float* q, int m, const float* db, int n, int n_valid, int d,
                     int k, int64_t idx_base, float* out_dist, int64_t* out_idx, void* stream) {
   IBL_REQUIRE(e && q && db && out_dist && out_idx, "null argument");

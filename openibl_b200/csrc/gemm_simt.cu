@@ -242,3 +242,16 @@ int launch_l2_normalize_rows(const float* x, int N, int D, float* out, cudaStrea
 }
 
 }  // namespace ibl
+
+namespace ibl {
+__global__ void scale_kernel(const float* __restrict__ x, float s, int n, float* __restrict__ y) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < n) y[i] = x[i] * s;
+}
+int launch_scale(const float* x, float s, int n, float* y, cudaStream_t st) {
+  if (n <= 0) return IBL_OK;
+  scale_kernel<<<cdiv(n, 256), 256, 0, st>>>(x, s, n, y);
+  IBL_CUDA_OK(cudaGetLastError());
+  return IBL_OK;
+}
+}  // namespace ibl

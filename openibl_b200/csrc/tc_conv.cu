@@ -122,7 +122,14 @@ conv3x3_tc_kernel(const __grid_constant__ CUtensorMap tm_xhi, const __grid_const
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 2 * STAGES + 4);
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  constexpr uint32_t TMEM_COLS = 2 * BN;  // 128, 256 or 512: a power of two >= 32
+  // BN = 64 (conv1_2): an M=128,N=64 MMA is bound by the 4 KiB shared-memory read of its A operand
+  // (128 B/clk).  B_hi and B_lo are adjacent in the stage, so ONE N=128 MMA  A_hi . [B_hi;B_lo]^T
+  // yields hi.hi (columns 0-63) and hi.lo (64-127) for a single read of A_hi; A_lo.B_hi goes to a
+  // third 64-column block.  Per 16-wide K step: 64 + 48 clk instead of 3 x 48.  The epilogue adds the
+  // three blocks.  ACC_COLS = TMEM columns per accumulator buffer.
+  constexpr bool kConcat = (BN == 64);
+  constexpr uint32_t ACC_COLS = kConcat ? 3 * BN : BN;
+  constexpr uint32_t TMEM_COLS = kConcat ? 512 : 2 * BN;  // a power of two >= 32
 
   if (warp == 0 && lane == 0) {
     tma_prefetch_desc(&tm_xhi);
@@ -194,7 +201,7 @@ conv3x3_tc_kernel(const __grid_constant__ CUtensorMap tm_xhi, const __grid_const
         const uint32_t aphase = (it >> 1) & 1;
         mbar_wait(&tempty_bar[as], aphase ^ 1);
         tc_fence_after();
-        const uint32_t d_tmem = tmem_base + as * BN;
+        const uint32_t d_tmem = tmem_base + as * ACC_COLS;
         for (int kit = 0; kit < kiters; ++kit) {
           mbar_wait(&full_bar[stage], phase);
           tc_fence_after();
@@ -207,9 +214,16 @@ conv3x3_tc_kernel(const __grid_constant__ CUtensorMap tm_xhi, const __grid_const
           for (int k = 0; k < TC_BK / 16; ++k) {
             // advance 16 bf16 = 32 bytes inside the 128-byte swizzle row: +2 in 16-byte units
             const uint64_t ko = (uint64_t)(k * 2);
-            umma_bf16(d_tmem, a_lo + ko, b_hi + ko, idesc, (kit > 0 || k > 0) ? 1u : 0u);
-            umma_bf16(d_tmem, a_hi + ko, b_lo + ko, idesc, 1u);
-            umma_bf16(d_tmem, a_hi + ko, b_hi + ko, idesc, 1u);
+            const uint32_t first = (kit > 0 || k > 0) ? 1u : 0u;
+            if (kConcat) {
+              constexpr uint32_t idesc2n = umma_idesc_bf16_f32(TC_BM, 2 * BN);
+              umma_bf16(d_tmem, a_hi + ko, b_hi + ko, idesc2n, first);          // [hi.hi | hi.lo]
+              umma_bf16(d_tmem + 2 * BN, a_lo + ko, b_hi + ko, idesc, first);   // lo.hi
+            } else {
+              umma_bf16(d_tmem, a_lo + ko, b_hi + ko, idesc, first);
+              umma_bf16(d_tmem, a_hi + ko, b_lo + ko, idesc, 1u);
+              umma_bf16(d_tmem, a_hi + ko, b_hi + ko, idesc, 1u);
+            }
           }
           umma_commit(&empty_bar[stage]);   // frees the smem slot when these MMAs retire
           if (++stage == STAGES) { stage = 0; phase ^= 1; }
@@ -247,12 +261,21 @@ conv3x3_tc_kernel(const __grid_constant__ CUtensorMap tm_xhi, const __grid_const
       }
       mbar_wait(&tfull_bar[as], aphase);
       tc_fence_after();
-      const uint32_t t_row = tmem_base + ((uint32_t)(q * 32) << 16) + as * BN;
+      const uint32_t t_row = tmem_base + ((uint32_t)(q * 32) << 16) + as * ACC_COLS;
       float ssq_acc = 0.f;   // per-pixel sum of squares over this N tile (feeds NetVLAD's input norm)
 #pragma unroll 1
       for (int ch = 0; ch < BN / 32; ++ch) {
         uint32_t raw[32];
         tmem_ld_32x32(t_row + ch * 32, raw);
+        if (kConcat) {   // add the hi.lo and lo.hi blocks (fp32, small terms first)
+          uint32_t r1[32], r2[32];
+          tmem_ld_32x32(t_row + BN + ch * 32, r1);
+          tmem_ld_32x32(t_row + 2 * BN + ch * 32, r2);
+          tmem_ld_wait();
+#pragma unroll
+          for (int j = 0; j < 32; ++j)
+            raw[j] = __float_as_uint((__uint_as_float(r1[j]) + __uint_as_float(r2[j])) + __uint_as_float(raw[j]));
+        }
         tmem_ld_wait();
         float v[32];
         const float4* bp = reinterpret_cast<const float4*>(a.bias + n0 + ch * 32);

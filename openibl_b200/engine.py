@@ -225,6 +225,13 @@ class Engine:
               "ibl_l2dist_dense")
         return out
 
+    def l2dist_self(self, x: torch.Tensor) -> torch.Tensor:
+        x = _require_cuda(x, "features")
+        n, d = x.shape
+        out = torch.empty(n, n, device=x.device)
+        check(self.lib.ibl_l2dist_self(self.h, _ptr(x), n, d, _ptr(out), _stream(self.device)), "ibl_l2dist_self")
+        return out
+
     def l2dist_topk(self, q: torch.Tensor, db: torch.Tensor, k: int, idx_base: int = 0,
                     n_valid: Optional[int] = None):
         q = _require_cuda(q, "queries")

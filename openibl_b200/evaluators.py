@@ -98,10 +98,7 @@ def pairwise_distance(features, query=None, gallery=None, metric=None):
         if metric is not None:
             x = metric.transform(x)
         xg = x.to(dev)
-        d = eng.l2dist_dense(xg, xg)                # |x_i|^2 + |x_j|^2 - 2 x_i.x_j
-        n2 = (xg * xg).sum(dim=1, keepdim=True)
-        d = d + (n2 - n2.t())                        # reference uses 2|x_i|^2 on every column (:110)
-        return d.cpu(), None, None
+        return eng.l2dist_self(xg).cpu(), None, None   # 2|x_i|^2 - 2 x_i.x_j, as the reference (:110-113)
     x = torch.stack([features[f] for f, _, _, _ in query]).view(len(query), -1)
     y = torch.stack([features[f] for f, _, _, _ in gallery]).view(len(gallery), -1)
     if metric is not None:
