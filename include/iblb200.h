@@ -101,6 +101,13 @@ int ibl_vgg16_forward(ibl_engine* e, const float* x_nchw, int N, int H, int W,
 int ibl_netvlad_forward(ibl_engine* e, const float* feat, int nhwc, int N, int C, int S,
                         const float* conv_w, const float* centroids, int K,
                         int normalize_input, float* vlad_raw, float* vlad_norm, void* stream);
+/* Backward of NetVLAD.forward (what autograd derives for netvlad.py:44-61; SURVEY 8 row a11, used by the SFRS
+ * training step, netvlad.py:139-146).  grad_vlad [N,K,C] -> grad_feat (same layout as feat), grad_conv_w [K,C],
+ * grad_centroids [K,C] (both summed over the batch).  fp32 CUDA cores; the soft-assignment is recomputed. */
+int ibl_netvlad_backward(ibl_engine* e, const float* feat, int nhwc, int N, int C, int S,
+                         const float* conv_w, const float* centroids, int K, int normalize_input,
+                         const float* grad_vlad, float* grad_feat, float* grad_conv_w,
+                         float* grad_centroids, void* stream);
 /* Only the two normalisations (netvlad.py:78-80): vlad_raw [N,K,C] -> out [N,K*C]. */
 int ibl_vlad_normalize(ibl_engine* e, const float* vlad_raw, int N, int K, int C,
                        float* out, void* stream);

@@ -34,6 +34,7 @@ SIGNATURES = {
     "ibl_engine_set_pca": (c_int, [_P, _P, _P, c_int, c_int, _P]),
     "ibl_vgg16_forward": (c_int, [_P, _P, c_int, c_int, c_int, _P, _P, _P, _P]),
     "ibl_netvlad_forward": (c_int, [_P, _P, c_int, c_int, c_int, c_int, _P, _P, c_int, c_int, _P, _P, _P]),
+    "ibl_netvlad_backward": (c_int, [_P, _P, c_int, c_int, c_int, c_int, _P, _P, c_int, c_int, _P, _P, _P, _P, _P]),
     "ibl_vlad_normalize": (c_int, [_P, _P, c_int, c_int, c_int, _P, _P]),
     "ibl_pca_l2": (c_int, [_P, _P, c_int, c_int, _P, _P, c_int, _P, _P]),
     "ibl_l2_normalize_rows": (c_int, [_P, _P, c_int, c_int, _P, _P]),

@@ -125,6 +125,13 @@ int launch_netvlad(const float* feat, bool nhwc, int N, int C, int S, const floa
                    float* invnorm, float* asum, float* vlad_raw, float* vlad_norm,
                    cudaStream_t s, uint64_t* launches);
 int launch_vlad_normalize(const float* raw, int N, int K, int C, float* out, cudaStream_t s);
+int launch_netvlad_assign(const float* feat, bool nhwc, int N, int C, int S, const float* conv_w,
+                          bool normalize_input, float* assign, float* invnorm, cudaStream_t s);
+// netvlad_bwd.cu
+int launch_netvlad_backward(const float* x, bool nhwc, int N, int C, int S, const float* conv_w,
+                            const float* centroids, const float* g, bool normalize_input, float* assign,
+                            float* invnorm, float* dz, float* part, int splits, float* dx, float* dW,
+                            float* dcent, cudaStream_t s, uint64_t* launches);
 
 // gemm_simt.cu  (C = A[m,K] . B[n,K]^T family)
 int launch_pca_l2(const float* v, int N, int D, const float* W, const float* b, int P,

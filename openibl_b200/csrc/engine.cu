@@ -391,6 +391,25 @@ int ibl_netvlad_forward(ibl_engine* e, const float* feat, int nhwc, int N, int C
                         S(stream), &e->launches);
 }
 
+int ibl_netvlad_backward(ibl_engine* e, const float* feat, int nhwc, int N, int C, int S_, const float* conv_w,
+                         const float* centroids, int K, int normalize_input, const float* grad_vlad,
+                         float* grad_feat, float* grad_conv_w, float* grad_centroids, void* stream) {
+  IBL_REQUIRE(e && feat && conv_w && centroids && grad_vlad && grad_feat && grad_conv_w && grad_centroids,
+              "null argument");
+  IBL_REQUIRE(N >= 1 && C >= 64 && S_ >= 1, "empty NetVLAD input");
+  IBL_REQUIRE(K == 64, "NetVLAD kernels are built for K=64 clusters");
+  DeviceGuard g(e->device);
+  const int splits = 64;
+  IBL_RET(e->nv_assign.ensure((size_t)N * S_ * K * sizeof(float)));
+  IBL_RET(e->nv_inv.ensure((size_t)N * S_ * sizeof(float)));
+  IBL_RET(e->nv_raw.ensure((size_t)N * S_ * K * sizeof(float)));                 // dz
+  IBL_RET(e->nv_part.ensure((size_t)splits * K * C * sizeof(float)));            // dW partials
+  return launch_netvlad_backward(feat, nhwc != 0, N, C, S_, conv_w, centroids, grad_vlad, normalize_input != 0,
+                                 e->nv_assign.as<float>(), e->nv_inv.as<float>(), e->nv_raw.as<float>(),
+                                 e->nv_part.as<float>(), splits, grad_feat, grad_conv_w, grad_centroids, S(stream),
+                                 &e->launches);
+}
+
 int ibl_vlad_normalize(ibl_engine* e, const float* vlad_raw, int N, int K, int C, float* out, void* stream) {
   IBL_REQUIRE(e && vlad_raw && out, "null argument");
   IBL_REQUIRE(N >= 1 && K >= 1 && C >= 1 && K <= 4096, "bad shape");

@@ -221,3 +221,18 @@ int launch_netvlad(const float* feat, bool nhwc, int N, int C, int S, const floa
 }
 
 }  // namespace ibl
+
+namespace ibl {
+// soft-assignment + inverse norms only (shared with the backward pass, netvlad_bwd.cu)
+int launch_netvlad_assign(const float* feat, bool nhwc, int N, int C, int S, const float* conv_w,
+                          bool normalize_input, float* assign, float* invnorm, cudaStream_t s) {
+  FeatView f;
+  f.p = feat;
+  f.sN = (long long)S * C;
+  if (nhwc) { f.sS = C; f.sC = 1; } else { f.sS = 1; f.sC = S; }
+  dim3 ga((unsigned)cdiv(S, 32), (unsigned)N);
+  netvlad_assign_kernel<<<ga, 256, 0, s>>>(f, nhwc, C, S, conv_w, normalize_input ? 1 : 0, assign, invnorm);
+  IBL_CUDA_OK(cudaGetLastError());
+  return IBL_OK;
+}
+}  // namespace ibl

@@ -162,6 +162,23 @@ class Engine:
                                            _stream(self.device)), "ibl_netvlad_forward")
         return raw, nrm
 
+    def netvlad_backward(self, feat: torch.Tensor, conv_w: torch.Tensor, centroids: torch.Tensor,
+                         grad_vlad: torch.Tensor, nhwc=False, normalize_input=True):
+        """-> (grad_feat like feat, grad_conv_w [K,C], grad_centroids [K,C])"""
+        feat = _require_cuda(feat, "feature map")
+        g = _require_cuda(grad_vlad, "grad_vlad")
+        K, C = centroids.shape
+        N, S = feat.shape[0], feat[0].numel() // C
+        w = _require_cuda(conv_w.detach().reshape(K, C), "net_vlad.conv.weight")
+        c = _require_cuda(centroids.detach(), "net_vlad.centroids")
+        dx = torch.empty_like(feat)
+        dw = torch.empty(K, C, device=feat.device)
+        dc = torch.empty(K, C, device=feat.device)
+        check(self.lib.ibl_netvlad_backward(self.h, _ptr(feat), 1 if nhwc else 0, N, C, S, _ptr(w), _ptr(c), K,
+                                            1 if normalize_input else 0, _ptr(g), _ptr(dx), _ptr(dw), _ptr(dc),
+                                            _stream(self.device)), "ibl_netvlad_backward")
+        return dx, dw, dc
+
     def vlad_normalize(self, raw: torch.Tensor) -> torch.Tensor:
         raw = _require_cuda(raw, "vlad")
         N, K, C = raw.shape

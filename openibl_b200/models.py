@@ -136,11 +136,35 @@ class NetVLAD(nn.Module):
         self.conv.weight.data.copy_(torch.from_numpy(self.alpha * assign).unsqueeze(2).unsqueeze(3))
 
     def forward(self, x):
-        _no_train(self, "NetVLAD.forward")
+        if torch.is_grad_enabled() and (x.requires_grad or self.conv.weight.requires_grad or self.centroids.requires_grad):
+            # training (SFRS region branch, netvlad.py:139-146): forward and backward both in libiblb200
+            return _NetVLADFunction.apply(x, self.conv.weight, self.centroids, self.normalize_input)
         eng = Engine.get(x.device)
         raw, _ = eng.netvlad_forward(x, self.conv.weight, self.centroids, nhwc=False,
                                      normalize_input=self.normalize_input, want_raw=True, want_norm=False)
         return raw
+
+
+class _NetVLADFunction(torch.autograd.Function):
+    """autograd bridge for NetVLAD: ibl_netvlad_forward / ibl_netvlad_backward."""
+
+    @staticmethod
+    def forward(ctx, x, conv_w, centroids, normalize_input):
+        eng = Engine.get(x.device)
+        xc = x.contiguous()
+        raw, _ = eng.netvlad_forward(xc, conv_w, centroids, nhwc=False, normalize_input=normalize_input,
+                                     want_raw=True, want_norm=False)
+        ctx.save_for_backward(xc, conv_w, centroids)
+        ctx.normalize_input = normalize_input
+        return raw
+
+    @staticmethod
+    def backward(ctx, grad_out):
+        x, conv_w, centroids = ctx.saved_tensors
+        eng = Engine.get(x.device)
+        dx, dw, dc = eng.netvlad_backward(x, conv_w, centroids, grad_out.contiguous(), nhwc=False,
+                                          normalize_input=ctx.normalize_input)
+        return dx, dw.view_as(conv_w), dc, None
 
 
 class _EmbedBase(nn.Module):

@@ -250,6 +250,32 @@ def test_netvlad_ragged_sizes_vs_oracle(eng, O):
     assert rel_l2(nrm.cpu(), O.vlad_normalize(want)) < 3e-5
 
 
+def test_netvlad_backward_vs_autograd_oracle(eng, O):
+    """gradients of NetVLAD.forward w.r.t. the feature map, the assignment weights and the
+    centroids, against torch autograd through the fp64 oracle (quarter-region sizes of the SFRS step: 15x20)."""
+    from ibl import models
+    gen = torch.Generator().manual_seed(21)
+    for sharp, (N, h, w) in ((False, (2, 7, 9)), (True, (3, 15, 20)), (True, (1, 5, 5))):
+        p = synth.make_netvlad_params(seed=4, sharp=sharp)
+        x = torch.randn(N, 512, h, w, generator=gen) * 2.0 + 0.3
+        G = torch.randn(N, 64, 512, generator=gen)
+        xd = x.double().requires_grad_(True)
+        wd = p["conv_weight"].double().requires_grad_(True)
+        cd = p["centroids"].double().requires_grad_(True)
+        (O.netvlad(xd, wd, cd) * G.double()).sum().backward()
+        layer = models.create("netvlad", dim=512).cuda().train()
+        layer.centroids.data.copy_(p["centroids"])
+        layer.conv.weight.data.copy_(p["conv_weight"])
+        xg = x.cuda().requires_grad_(True)
+        out = layer(xg)
+        assert out.requires_grad and rel_l2(out.detach().cpu(), O.netvlad(x, p["conv_weight"], p["centroids"])) < 3e-5
+        (out * G.cuda()).sum().backward()
+        tol = 3e-4 if sharp else 5e-5      # sharp softmax (alpha ~ 280) amplifies fp32 rounding in dz
+        assert rel_l2(xg.grad.cpu(), xd.grad) < tol, (sharp, N, h, w, rel_l2(xg.grad.cpu(), xd.grad))
+        assert rel_l2(layer.conv.weight.grad.cpu(), wd.grad) < tol, (sharp, rel_l2(layer.conv.weight.grad.cpu(), wd.grad))
+        assert rel_l2(layer.centroids.grad.cpu(), cd.grad) < tol, (sharp, rel_l2(layer.centroids.grad.cpu(), cd.grad))
+
+
 # ---------------------------------------------------------------------------------------------
 # stage (iii-a): PCA-whiten + L2
 # ---------------------------------------------------------------------------------------------
