@@ -209,17 +209,55 @@ class EmbedNetPCA(_EmbedBase):
 
 
 class EmbedRegionNet(_EmbedBase):
-    """netvlad.py:112-207.  Eval branch (:199-205) only; the train branch needs NetVLAD backward."""
+    """netvlad.py:112-207.  Eval: (pool, vlad) like EmbedNet (:199-205).  Train: the SFRS region branch
+    (:123-194) -- quarter / half / global region VLADs of the anchor and of every pair image and their 9x9
+    similarity matrix.  NetVLAD runs (forward and backward) in libiblb200; the VGG trunk is evaluated by the
+    engine without a graph, i.e. it is treated as frozen (conv backward kernels are not built yet), so only
+    `net_vlad.*` receives gradients."""
 
     def __init__(self, base_model, net_vlad, tuple_size=1):
         super().__init__(base_model, net_vlad)
         self.tuple_size = tuple_size
 
+    @staticmethod
+    def _quarters(feat):
+        # [N,C,H,W] -> [N*4,C,H/2,W/2], region order (top-left, top-right, bottom-left, bottom-right)
+        N, C, H, W = feat.shape
+        h2, w2 = H // 2, W // 2
+        q = feat[:, :, : 2 * h2, : 2 * w2].reshape(N, C, 2, h2, 2, w2).permute(0, 2, 4, 1, 3, 5)
+        return q.reshape(N * 4, C, h2, w2).contiguous()
+
+    def _region_descriptors(self, feat):
+        # -> [N, 9, K*C]: global, 4 halves (top, bottom, left, right), 4 quarters; intra-norm + L2 each
+        N = feat.shape[0]
+        quarter = self.net_vlad(self._quarters(feat))                       # [(N*4), K, C]
+        K, C = quarter.shape[1:]
+        quarter = quarter.view(N, 4, K, C)
+        half = torch.stack((quarter[:, 0] + quarter[:, 1], quarter[:, 2] + quarter[:, 3],
+                            quarter[:, 0] + quarter[:, 2], quarter[:, 1] + quarter[:, 3]), dim=1)
+        whole = quarter.sum(dim=1, keepdim=True)
+        v = torch.cat((whole, half, quarter), dim=1)                        # [N, 9, K, C]
+        v = torch.nn.functional.normalize(v, p=2, dim=3).reshape(N, 9, K * C)
+        return torch.nn.functional.normalize(v, p=2, dim=2)
+
+    def _forward_train(self, feat):
+        B, C, H, W = feat.shape
+        t = feat.view(self.tuple_size, -1, C, H, W)
+        anchors = t[:, 0].contiguous()                                      # [T,C,H,W]
+        pairs = t[:, 1:].reshape(-1, C, H, W)                               # [T*(n-1),C,H,W]
+        va = self._region_descriptors(anchors).view(self.tuple_size, 1, 9, -1)
+        vb = self._region_descriptors(pairs).view(self.tuple_size, -1, 9, va.shape[-1])
+        score = torch.matmul(va, vb.transpose(2, 3))                        # [T, n-1, 9, 9] (anchor broadcast)
+        return score, va, vb
+
     def forward(self, x):
-        _no_train(self, "EmbedRegionNet.forward (train branch)")
         eng = self._bind(x)
-        vlad, pool = eng.extract(x, pca=False, want_pool=True)
-        return pool, vlad
+        if not self.training:
+            vlad, pool = eng.extract(x, pca=False, want_pool=True)
+            return pool, vlad
+        with torch.no_grad():
+            _, feat, _ = eng.vgg16_forward(x, want_nchw=True, want_pool=False)
+        return self._forward_train(feat)
 
 
 _factory = {

@@ -276,6 +276,36 @@ def test_netvlad_backward_vs_autograd_oracle(eng, O):
         assert rel_l2(layer.centroids.grad.cpu(), cd.grad) < tol, (sharp, rel_l2(layer.centroids.grad.cpu(), cd.grad))
 
 
+def test_embedregionnet_train_branch_vs_reference(eng):
+    """SFRS region branch (netvlad.py:123-207) in train mode against the unmodified reference run on CPU
+    (tests/golden/region_train.npz): 9x9 region similarities, region descriptors, and the gradients of a scalar
+    loss w.r.t. the NetVLAD parameters (the VGG trunk is frozen here, so only those are compared)."""
+    from ibl import models
+    g = load_golden("region_train")
+    sd = synth.make_state_dict(seed=13, sharp=True, with_pca=False, bias_scale=0.02)
+    base = models.create("vgg16", pretrained=False)
+    pool = models.create("netvlad", dim=512)
+    model = models.create("embedregionnet", base, pool, tuple_size=1)
+    model.load_state_dict(sd)
+    model = model.cuda().train()
+    x = synth.make_images(seed=14, batch=5, height=64, width=96).cuda()
+    score, va, vb = model(x)
+    assert tuple(score.shape) == (1, 4, 9, 9) and tuple(va.shape) == (1, 1, 9, 32768) and tuple(vb.shape) == (1, 4, 9, 32768)
+    assert np.abs(score.detach().cpu().numpy() - g["score"]).max() < 2e-4          # cosine similarities in [-1,1]
+    assert rel_l2(va.detach().cpu()[..., ::16], g["vlad_a"]) < DESC_TOL
+    assert rel_l2(vb.detach().cpu()[..., ::16], g["vlad_b"]) < DESC_TOL
+    loss = (score * torch.from_numpy(g["loss_weights"]).cuda()).sum()
+    assert abs(loss.item() - float(g["loss"])) < 2e-3 * max(1.0, abs(float(g["loss"])))
+    loss.backward()
+    assert rel_l2(model.net_vlad.centroids.grad.cpu(), g["grad_centroids"]) < 2e-3
+    assert rel_l2(model.net_vlad.conv.weight.grad.cpu(), g["grad_conv_w"]) < 2e-3
+    # eval branch unchanged: (pool, vlad)
+    model.eval()
+    with torch.no_grad():
+        pool_x, vlad_x = model(x)
+    assert tuple(pool_x.shape) == (5, 512) and tuple(vlad_x.shape) == (5, 32768)
+
+
 # ---------------------------------------------------------------------------------------------
 # stage (iii-a): PCA-whiten + L2
 # ---------------------------------------------------------------------------------------------
