@@ -77,6 +77,21 @@ __device__ __forceinline__ void tma_load_4d(void* dst, const CUtensorMap* m, uin
       : "memory");
 }
 
+// 2D tiled load delivered to every CTA of the cluster whose bit is set in `mask` (same smem offset and same
+// mbarrier offset in each destination CTA)
+__device__ __forceinline__ void tma_load_2d_mc(void* dst, const CUtensorMap* m, uint64_t* bar, int c0, int c1,
+                                               uint16_t mask) {
+  asm volatile(
+      "cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes.multicast::cluster"
+      " [%0], [%1, {%4, %5}], [%2], %3;" ::"r"(smem_u32(dst)),
+      "l"(reinterpret_cast<uint64_t>(m)), "r"(smem_u32(bar)), "h"(mask), "r"(c0), "r"(c1)
+      : "memory");
+}
+__device__ __forceinline__ void cluster_sync_all() {
+  asm volatile("barrier.cluster.arrive.release.aligned;" ::: "memory");
+  asm volatile("barrier.cluster.wait.acquire.aligned;" ::: "memory");
+}
+
 // fire-and-forget: bring one box into L2
 __device__ __forceinline__ void tma_prefetch_3d(const CUtensorMap* m, int c0, int c1, int c2) {
   asm volatile("cp.async.bulk.prefetch.tensor.3d.L2.global [%0, {%1, %2, %3}];" ::"l"(
@@ -117,6 +132,20 @@ __device__ __forceinline__ uint64_t umma_desc_kmajor_sw128(uint32_t smem_addr) {
   d |= (uint64_t)1 << 46;                           // descriptor version (Blackwell)
   d |= (uint64_t)2 << 61;                           // layout type: SWIZZLE_128B
   return d;
+}
+// Same with 64-byte rows (32 bf16) and the 64B swizzle: 8-row atoms are 512 bytes.
+__device__ __forceinline__ uint64_t umma_desc_kmajor_sw64(uint32_t smem_addr) {
+  uint64_t d = 0;
+  d |= (uint64_t)((smem_addr >> 4) & 0x3fffu);
+  d |= (uint64_t)1 << 16;
+  d |= (uint64_t)(512u >> 4) << 32;
+  d |= (uint64_t)1 << 46;
+  d |= (uint64_t)4 << 61;                           // layout type: SWIZZLE_64B
+  return d;
+}
+template <int BK>
+__device__ __forceinline__ uint64_t umma_desc_kmajor(uint32_t smem_addr) {
+  return BK == 64 ? umma_desc_kmajor_sw128(smem_addr) : umma_desc_kmajor_sw64(smem_addr);
 }
 // Instruction descriptor for kind::f16 with bf16 A/B (K-major), fp32 accumulator
 // (cute::UMMA::InstrDescriptor).
@@ -161,6 +190,15 @@ __device__ __forceinline__ void umma_commit(uint64_t* bar) {
                : "memory");
 }
 
+// same, arriving on the barrier at this offset in every CTA of the cluster selected by `mask`
+__device__ __forceinline__ void umma_commit_mc(uint64_t* bar, uint16_t mask) {
+  asm volatile(
+      "tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], %1;" ::"r"(
+          smem_u32(bar)),
+      "h"(mask)
+      : "memory");
+}
+
 // TMEM -> registers: this warp's 32 lanes x 32 consecutive fp32 columns
 __device__ __forceinline__ void tmem_ld_32x32(uint32_t taddr, uint32_t (&r)[32]) {
   asm volatile(
@@ -189,7 +227,7 @@ EncodeTiledFn get_encode_tiled();
 // rank-`rank` tiled map with 128B swizzle; dims/strides innermost first (strides in bytes for
 // dims 1..rank-1).
 int make_tmap(CUtensorMap* out, CUtensorMapDataType dt, int rank, const void* base,
-              const uint64_t* dims, const uint64_t* strides_bytes, const uint32_t* box);
+              const uint64_t* dims, const uint64_t* strides_bytes, const uint32_t* box, int swizzle_bytes = 128);
 
 }  // namespace tc
 }  // namespace ibl

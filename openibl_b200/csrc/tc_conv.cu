@@ -45,7 +45,7 @@ EncodeTiledFn get_encode_tiled() {
 }
 
 int make_tmap(CUtensorMap* out, CUtensorMapDataType dt, int rank, const void* base,
-              const uint64_t* dims, const uint64_t* strides_bytes, const uint32_t* box) {
+              const uint64_t* dims, const uint64_t* strides_bytes, const uint32_t* box, int swizzle_bytes) {
   EncodeTiledFn enc = get_encode_tiled();
   if (!enc) {
     set_last_error("cuTensorMapEncodeTiled is not available (no CUDA driver?)");
@@ -61,7 +61,8 @@ int make_tmap(CUtensorMap* out, CUtensorMapDataType dt, int rank, const void* ba
   }
   for (int i = 0; i + 1 < rank; ++i) gstr[i] = strides_bytes[i];
   CUresult r = enc(out, dt, (cuuint32_t)rank, const_cast<void*>(base), gdim, gstr, bx, es,
-                   CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B,
+                   CU_TENSOR_MAP_INTERLEAVE_NONE,
+                   swizzle_bytes == 64 ? CU_TENSOR_MAP_SWIZZLE_64B : CU_TENSOR_MAP_SWIZZLE_128B,
                    CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
   if (r != CUDA_SUCCESS) {
     set_last_error("cuTensorMapEncodeTiled failed with CUresult " + std::to_string((int)r));

@@ -41,15 +41,28 @@ struct GemmTcArgs {
 
 constexpr int GT_BM = 128, GT_BK = 64, GT_A_BYTES = GT_BM * GT_BK * 2;
 
-template <int BN, int STAGES, int EPI>
+// MC = true: the grid is launched as clusters of two CTAs that walk the same column tiles with adjacent
+// row tiles.  Each CTA fetches only half of every B tile and TMA-multicasts it into both CTAs' shared
+// memory, so the per-SM L2->SM operand traffic drops from A+B to A+B/2 per K chunk (the kernel is bound by
+// the L2 latency x bandwidth product against the ~190 KiB of stages that fit, profiles/r01_dist_tc.md).
+// A stage may be refilled only when BOTH CTAs' MMAs have released it: the MMA warp's tcgen05.commit is
+// multicast to the empty barrier of both CTAs (arrival count 2).
+template <int BN, int STAGES, int EPI, bool MC, int BK = 64>
 __global__ void __launch_bounds__(192, 1)
 gemm_tc_kernel(const __grid_constant__ CUtensorMap tm_ahi, const __grid_constant__ CUtensorMap tm_alo,
                const __grid_constant__ CUtensorMap tm_bhi, const __grid_constant__ CUtensorMap tm_blo,
                const GemmTcArgs g) {
+  constexpr int CL = MC ? 2 : 1;
+  uint32_t cta_rank = 0;
+  if (MC) asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(cta_rank));
+  const int unit0 = blockIdx.x / CL, unit_stride = gridDim.x / CL;   // a unit = one CTA or one CTA pair
   extern __shared__ __align__(1024) uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
-  constexpr int B_BYTES = BN * GT_BK * 2;
-  constexpr int STAGE_BYTES = 2 * GT_A_BYTES + 2 * B_BYTES;
+  // BK = 64: 128-byte rows, 128B swizzle.  BK = 32: 64-byte rows, 64B swizzle -- half-size stages, so a
+  // 256-column tile still gets a 4-deep pipeline.
+  constexpr int A_BYTES = GT_BM * BK * 2;
+  constexpr int B_BYTES = BN * BK * 2;
+  constexpr int STAGE_BYTES = 2 * A_BYTES + 2 * B_BYTES;
   uint64_t* bars = reinterpret_cast<uint64_t*>(smem + STAGES * STAGE_BYTES);
   uint64_t* full_bar = bars;
   uint64_t* empty_bar = bars + STAGES;
@@ -66,7 +79,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tm_ahi, const __grid_constant
     tma_prefetch_desc(&tm_blo);
     for (int i = 0; i < STAGES; ++i) {
       mbar_init(&full_bar[i], 1);
-      mbar_init(&empty_bar[i], 1);
+      mbar_init(&empty_bar[i], CL);
     }
     mbar_init(&tfull_bar[0], 1);
     mbar_init(&tfull_bar[1], 1);
@@ -81,22 +94,25 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tm_ahi, const __grid_constant
   }
   tc_fence_before();
   __syncthreads();
+  if (MC) cluster_sync_all();     // the peer's barriers exist before anything is multicast into this CTA
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
 
-  // item -> (row tile, first column tile, #column tiles, first K chunk, #K chunks)
+  // item -> (row tile, first column tile, #column tiles, first K chunk, #K chunks); with MC an item is a
+  // pair of adjacent row tiles and this CTA takes the one matching its rank in the cluster
   auto decode = [&](int item, int& mt, int& nt0, int& ntn, int& k0, int& kn) {
     mt = item / g.items_per_mtile;
     const int sub = item - mt * g.items_per_mtile;
+    mt = mt * CL + (int)cta_rank;
     if (EPI == EPI_PARTIAL) {
       nt0 = 0; ntn = g.n_tiles;
       k0 = sub * g.kit_per_item;
-      const int ktot = g.K / GT_BK;
+      const int ktot = g.K / BK;
       kn = (k0 + g.kit_per_item <= ktot) ? g.kit_per_item : (ktot - k0);
     } else {
       nt0 = sub * g.nt_per_item;
       ntn = (nt0 + g.nt_per_item <= g.n_tiles) ? g.nt_per_item : (g.n_tiles - nt0);
-      k0 = 0; kn = g.K / GT_BK;
+      k0 = 0; kn = g.K / BK;
     }
   };
 
@@ -104,7 +120,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tm_ahi, const __grid_constant
     if (lane == 0) {
       int stage = 0;
       uint32_t phase = 0;
-      for (int item = blockIdx.x; item < g.total_items; item += gridDim.x) {
+      for (int item = unit0; item < g.total_items; item += unit_stride) {
         int mt, nt0, ntn, k0, kn;
         decode(item, mt, nt0, ntn, k0, kn);
         for (int nt = nt0; nt < nt0 + ntn; ++nt) {
@@ -112,10 +128,18 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tm_ahi, const __grid_constant
             mbar_wait(&empty_bar[stage], phase ^ 1);
             uint8_t* st = smem + stage * STAGE_BYTES;
             mbar_arrive_expect_tx(&full_bar[stage], STAGE_BYTES);
-            tma_load_2d(st, &tm_ahi, &full_bar[stage], kit * GT_BK, mt * GT_BM);
-            tma_load_2d(st + GT_A_BYTES, &tm_alo, &full_bar[stage], kit * GT_BK, mt * GT_BM);
-            tma_load_2d(st + 2 * GT_A_BYTES, &tm_bhi, &full_bar[stage], kit * GT_BK, nt * BN);
-            tma_load_2d(st + 2 * GT_A_BYTES + B_BYTES, &tm_blo, &full_bar[stage], kit * GT_BK, nt * BN);
+            tma_load_2d(st, &tm_ahi, &full_bar[stage], kit * BK, mt * GT_BM);
+            tma_load_2d(st + A_BYTES, &tm_alo, &full_bar[stage], kit * BK, mt * GT_BM);
+            if (MC) {   // this CTA's half of the B tile, delivered to both CTAs of the pair
+              constexpr int HB = B_BYTES / 2;
+              tma_load_2d_mc(st + 2 * A_BYTES + cta_rank * HB, &tm_bhi, &full_bar[stage], kit * BK,
+                             nt * BN + (int)cta_rank * (BN / 2), 0x3);
+              tma_load_2d_mc(st + 2 * A_BYTES + B_BYTES + cta_rank * HB, &tm_blo, &full_bar[stage],
+                             kit * BK, nt * BN + (int)cta_rank * (BN / 2), 0x3);
+            } else {
+              tma_load_2d(st + 2 * A_BYTES, &tm_bhi, &full_bar[stage], kit * BK, nt * BN);
+              tma_load_2d(st + 2 * A_BYTES + B_BYTES, &tm_blo, &full_bar[stage], kit * BK, nt * BN);
+            }
             if (++stage == STAGES) { stage = 0; phase ^= 1; }
           }
         }
@@ -127,7 +151,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tm_ahi, const __grid_constant
       int stage = 0;
       uint32_t phase = 0;
       int it = 0;
-      for (int item = blockIdx.x; item < g.total_items; item += gridDim.x) {
+      for (int item = unit0; item < g.total_items; item += unit_stride) {
         int mt, nt0, ntn, k0, kn;
         decode(item, mt, nt0, ntn, k0, kn);
         for (int nt = nt0; nt < nt0 + ntn; ++nt, ++it) {
@@ -140,18 +164,19 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tm_ahi, const __grid_constant
             mbar_wait(&full_bar[stage], phase);
             tc_fence_after();
             const uint32_t sa = smem_u32(smem + stage * STAGE_BYTES);
-            const uint64_t a_hi = umma_desc_kmajor_sw128(sa);
-            const uint64_t a_lo = umma_desc_kmajor_sw128(sa + GT_A_BYTES);
-            const uint64_t b_hi = umma_desc_kmajor_sw128(sa + 2 * GT_A_BYTES);
-            const uint64_t b_lo = umma_desc_kmajor_sw128(sa + 2 * GT_A_BYTES + B_BYTES);
+            const uint64_t a_hi = umma_desc_kmajor<BK>(sa);
+            const uint64_t a_lo = umma_desc_kmajor<BK>(sa + A_BYTES);
+            const uint64_t b_hi = umma_desc_kmajor<BK>(sa + 2 * A_BYTES);
+            const uint64_t b_lo = umma_desc_kmajor<BK>(sa + 2 * A_BYTES + B_BYTES);
 #pragma unroll
-            for (int k = 0; k < GT_BK / 16; ++k) {
+            for (int k = 0; k < BK / 16; ++k) {
               const uint64_t ko = (uint64_t)(k * 2);
               umma_bf16(d_tmem, a_lo + ko, b_hi + ko, idesc, (kit > 0 || k > 0) ? 1u : 0u);
               umma_bf16(d_tmem, a_hi + ko, b_lo + ko, idesc, 1u);
               umma_bf16(d_tmem, a_hi + ko, b_hi + ko, idesc, 1u);
             }
-            umma_commit(&empty_bar[stage]);
+            if (MC) umma_commit_mc(&empty_bar[stage], 0x3);   // frees the slot in both CTAs of the pair
+            else umma_commit(&empty_bar[stage]);
             if (++stage == STAGES) { stage = 0; phase ^= 1; }
           }
           umma_commit(&tfull_bar[as]);
@@ -162,7 +187,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tm_ahi, const __grid_constant
     const int q = warp & 3;
     const int rloc = q * 32 + lane;
     int it = 0;
-    for (int item = blockIdx.x; item < g.total_items; item += gridDim.x) {
+    for (int item = unit0; item < g.total_items; item += unit_stride) {
       int mt, nt0, ntn, k0, kn;
       decode(item, mt, nt0, ntn, k0, kn);
       const int row = mt * GT_BM + rloc;
@@ -188,7 +213,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tm_ahi, const __grid_constant
           tmem_ld_wait();
           const int col0 = nt * BN + ch * 32;
           if (EPI == EPI_PARTIAL) {
-            const int split = item - mt * g.items_per_mtile;
+            const int split = item % g.items_per_mtile;
             float* o = g.out + ((long long)split * g.N) * g.M;
             if (row_ok) {
 #pragma unroll
@@ -241,7 +266,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tm_ahi, const __grid_constant
         if (lane == 0) mbar_arrive(&tempty_bar[as]);
       }
       if (EPI == EPI_TOP16 && row_ok) {
-        const int sub = item - mt * g.items_per_mtile;
+        const int sub = item % g.items_per_mtile;
         float* od = g.cand_d + ((long long)sub * g.M + row) * 16;
         long long* oi = g.cand_i + ((long long)sub * g.M + row) * 16;
 #pragma unroll
@@ -252,6 +277,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tm_ahi, const __grid_constant
 
   tc_fence_before();
   __syncthreads();
+  if (MC) cluster_sync_all();     // no CTA leaves while its peer may still multicast into it or arrive on its barriers
   if (warp == 1) {
     tc_fence_after();
     tmem_dealloc(tmem_base, TMEM_COLS);
@@ -270,36 +296,56 @@ static int sm_count() {
   return sms;
 }
 
-template <int BN, int STAGES, int EPI>
+template <int BN, int STAGES, int EPI, bool MC = false, int BK = 64>
 static int launch_gemm_variant(const CUtensorMap* maps, const GemmTcArgs& g, cudaStream_t s) {
-  constexpr int smem = STAGES * (2 * GT_A_BYTES + 2 * BN * GT_BK * 2) + 1024 + 256;
+  constexpr int smem = STAGES * (2 * GT_BM * BK * 2 + 2 * BN * BK * 2) + 1024 + 256;
   static bool attr_done = false;
   if (!attr_done) {
-    IBL_CUDA_OK(cudaFuncSetAttribute(gemm_tc_kernel<BN, STAGES, EPI>,
+    IBL_CUDA_OK(cudaFuncSetAttribute(gemm_tc_kernel<BN, STAGES, EPI, MC, BK>,
                                      cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
     attr_done = true;
   }
-  const int grid = g.total_items < sm_count() ? g.total_items : sm_count();
-  gemm_tc_kernel<BN, STAGES, EPI><<<grid, 192, smem, s>>>(maps[0], maps[1], maps[2], maps[3], g);
-  IBL_CUDA_OK(cudaGetLastError());
+  if (!MC) {
+    const int grid = g.total_items < sm_count() ? g.total_items : sm_count();
+    gemm_tc_kernel<BN, STAGES, EPI, false, BK><<<grid, 192, smem, s>>>(maps[0], maps[1], maps[2], maps[3], g);
+    IBL_CUDA_OK(cudaGetLastError());
+    return IBL_OK;
+  }
+  // clusters of two CTAs; g.total_items counts PAIRS of row tiles
+  const int pairs = sm_count() / 2;
+  const int units = g.total_items < pairs ? g.total_items : pairs;
+  cudaLaunchConfig_t cfg{};
+  cfg.gridDim = dim3(2 * units);
+  cfg.blockDim = dim3(192);
+  cfg.dynamicSmemBytes = smem;
+  cfg.stream = s;
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeClusterDimension;
+  attr[0].val.clusterDim.x = 2;
+  attr[0].val.clusterDim.y = 1;
+  attr[0].val.clusterDim.z = 1;
+  cfg.attrs = attr;
+  cfg.numAttrs = 1;
+  IBL_CUDA_OK(cudaLaunchKernelEx(&cfg, gemm_tc_kernel<BN, STAGES, EPI, true, BK>, maps[0], maps[1], maps[2], maps[3], g));
   return IBL_OK;
 }
 
 static int make_plane_maps(CUtensorMap* maps, const __nv_bfloat16* a_hi, const __nv_bfloat16* a_lo, int M,
-                           const __nv_bfloat16* b_hi, const __nv_bfloat16* b_lo, int N, int K, int bn) {
+                           const __nv_bfloat16* b_hi, const __nv_bfloat16* b_lo, int N, int K, int bn, int bk = 64) {
   uint64_t dims_a[2] = {(uint64_t)K, (uint64_t)M}, dims_b[2] = {(uint64_t)K, (uint64_t)N};
   uint64_t str[1] = {(uint64_t)K * 2};
-  uint32_t box_a[2] = {64, 128}, box_b[2] = {64, (uint32_t)bn};
-  IBL_RET(make_tmap(&maps[0], CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, a_hi, dims_a, str, box_a));
-  IBL_RET(make_tmap(&maps[1], CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, a_lo, dims_a, str, box_a));
-  IBL_RET(make_tmap(&maps[2], CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, b_hi, dims_b, str, box_b));
-  IBL_RET(make_tmap(&maps[3], CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, b_lo, dims_b, str, box_b));
+  uint32_t box_a[2] = {(uint32_t)bk, 128}, box_b[2] = {(uint32_t)bk, (uint32_t)bn};
+  const int sw = bk == 64 ? 128 : 64;
+  IBL_RET(make_tmap(&maps[0], CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, a_hi, dims_a, str, box_a, sw));
+  IBL_RET(make_tmap(&maps[1], CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, a_lo, dims_a, str, box_a, sw));
+  IBL_RET(make_tmap(&maps[2], CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, b_hi, dims_b, str, box_b, sw));
+  IBL_RET(make_tmap(&maps[3], CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, b_lo, dims_b, str, box_b, sw));
   return IBL_OK;
 }
 
 // choose the number of column runs per row tile so the round-robin deal fills whole waves
-static int pick_runs(int m_tiles, int n_tiles, int min_tiles_per_run) {
-  const int G = sm_count();
+static int pick_runs(int m_tiles, int n_tiles, int min_tiles_per_run, int units = 0) {
+  const int G = units > 0 ? units : sm_count();
   int best = 1;
   double best_eff = -1.0;
   const int rmax = n_tiles / (min_tiles_per_run > 0 ? min_tiles_per_run : 1);
@@ -316,12 +362,16 @@ static int pick_runs(int m_tiles, int n_tiles, int min_tiles_per_run) {
 }
 
 // Distance + running top-16 per (query, column run): cand_* [runs][M][16]; returns runs.
-// N tile of the distance kernel.  The kernel is bound by L2->SM operand traffic (profiles/r01_dist_tc.md);
-// a 256-column tile (IBL_DIST_BN=256) halves the re-read of the query tile but only fits 2 pipeline
-// stages, and measured the same 1.91 ms as 128 columns x 3 stages on 6.8k x 10k x 4096 -- 128 stays default.
+// Tile shape of the distance kernel (measured on 6.8k x 10k x 4096, whole retrieval call, same process):
+//   BN=128, BK=64 (128B swizzle), 3 stages                      1.945 ms
+//   BN=128, BK=64, 3 stages, CTA pairs + TMA multicast of B     1.890 ms   (IBL_DIST_BN=128 IBL_GEMM_MC=1)
+//   BN=256, BK=32 (64B swizzle), 4 stages                       1.846 ms   (default)
+// A 256-column tile needs 96 instead of 128 B/clk of shared-memory operand reads per MMA, and the half-size
+// K chunk keeps a 4-deep pipeline inside 192 KiB.  All three land near 1.3 ms for the GEMM itself
+// (~1285 TF/s of issued bf16 MMA, ~0.89 of the power-capped cuBLAS rate).
 static int dist_bn() {
   static int bn = 0;
-  if (!bn) { const char* v = getenv("IBL_DIST_BN"); bn = (v && atoi(v) == 256) ? 256 : 128; }
+  if (!bn) { const char* v = getenv("IBL_DIST_BN"); bn = (v && atoi(v) == 128) ? 128 : 256; }
   return bn;
 }
 
@@ -331,29 +381,36 @@ int launch_dist_top16_tc(const __nv_bfloat16* q_hi, const __nv_bfloat16* q_lo, c
                          cudaStream_t s) {
   IBL_REQUIRE(K % 64 == 0, "tcgen05 distance needs dim % 64 == 0");
   const int BN = dist_bn();
+  const int m_tiles = cdiv(m, GT_BM);
+  const bool mc = gemm_mc() && BN == 128 && m_tiles >= 2;
+  const int bk = BN == 256 ? 32 : 64;
   CUtensorMap maps[4];
-  IBL_RET(make_plane_maps(maps, q_hi, q_lo, m, d_hi, d_lo, n, K, BN));
+  IBL_RET(make_plane_maps(maps, q_hi, q_lo, m, d_hi, d_lo, n, K, mc ? BN / 2 : BN, bk));
   GemmTcArgs g{};
   g.M = m; g.N = n; g.K = K;
   g.n_tiles = cdiv(n_valid > 0 ? n_valid : 1, BN);
-  const int m_tiles = cdiv(m, GT_BM);
-  int runs = pick_runs(m_tiles, g.n_tiles, BN == 256 ? 1 : 2);
+  const int m_units = mc ? cdiv(m_tiles, 2) : m_tiles;
+  int runs = pick_runs(m_units, g.n_tiles, BN == 256 ? 1 : 2, mc ? sm_count() / 2 : 0);
   if (runs > max_runs) runs = max_runs;
   g.nt_per_item = cdiv(g.n_tiles, runs);
   g.items_per_mtile = cdiv(g.n_tiles, g.nt_per_item);
-  g.kit_per_item = K / 64;
-  g.total_items = m_tiles * g.items_per_mtile;
+  g.kit_per_item = K / bk;
+  g.total_items = m_units * g.items_per_mtile;
   g.n_valid = n_valid;
   g.an = qn; g.bn = dn;
   g.cand_d = cand_d; g.cand_i = cand_i;
   *runs_out = g.items_per_mtile;
-  if (BN == 256) return launch_gemm_variant<256, 2, EPI_TOP16>(maps, g, s);
+  if (mc) return launch_gemm_variant<128, 3, EPI_TOP16, true>(maps, g, s);
+  if (BN == 256) return launch_gemm_variant<256, 4, EPI_TOP16, false, 32>(maps, g, s);
   return launch_gemm_variant<128, 3, EPI_TOP16>(maps, g, s);
 }
 
 int dist_top16_max_runs(int m, int n_valid) {
   const int BN = dist_bn();
-  return pick_runs(cdiv(m, GT_BM), cdiv(n_valid > 0 ? n_valid : 1, BN), BN == 256 ? 1 : 2);
+  const int m_tiles = cdiv(m, GT_BM);
+  const bool mc = gemm_mc() && BN == 128 && m_tiles >= 2;
+  return pick_runs(mc ? cdiv(m_tiles, 2) : m_tiles, cdiv(n_valid > 0 ? n_valid : 1, BN), BN == 256 ? 1 : 2,
+                   mc ? sm_count() / 2 : 0);
 }
 
 int launch_dist_dense_tc(const __nv_bfloat16* q_hi, const __nv_bfloat16* q_lo, const float* qn, int m,
@@ -361,20 +418,23 @@ int launch_dist_dense_tc(const __nv_bfloat16* q_hi, const __nv_bfloat16* q_lo, c
                          float* out, long long ld_out, cudaStream_t s) {
   IBL_REQUIRE(K % 64 == 0, "tcgen05 distance needs dim % 64 == 0");
   constexpr int BN = 128;
+  const int m_tiles = cdiv(m, GT_BM);
+  const bool mc = gemm_mc() && m_tiles >= 2;
   CUtensorMap maps[4];
-  IBL_RET(make_plane_maps(maps, q_hi, q_lo, m, d_hi, d_lo, n, K, BN));
+  IBL_RET(make_plane_maps(maps, q_hi, q_lo, m, d_hi, d_lo, n, K, mc ? BN / 2 : BN));
   GemmTcArgs g{};
   g.M = m; g.N = n; g.K = K;
   g.n_tiles = cdiv(n, BN);
-  const int m_tiles = cdiv(m, GT_BM);
-  const int runs = pick_runs(m_tiles, g.n_tiles, 1);
+  const int m_units = mc ? cdiv(m_tiles, 2) : m_tiles;
+  const int runs = pick_runs(m_units, g.n_tiles, 1, mc ? sm_count() / 2 : 0);
   g.nt_per_item = cdiv(g.n_tiles, runs);
   g.items_per_mtile = cdiv(g.n_tiles, g.nt_per_item);
   g.kit_per_item = K / 64;
-  g.total_items = m_tiles * g.items_per_mtile;
+  g.total_items = m_units * g.items_per_mtile;
   g.n_valid = n;
   g.an = qn; g.bn = dn;
   g.out = out; g.ld_out = ld_out;
+  if (mc) return launch_gemm_variant<BN, 3, EPI_DENSE, true>(maps, g, s);
   return launch_gemm_variant<BN, 3, EPI_DENSE>(maps, g, s);
 }
 
