@@ -369,6 +369,13 @@ static int pick_runs(int m_tiles, int n_tiles, int min_tiles_per_run, int units 
 // A 256-column tile needs 96 instead of 128 B/clk of shared-memory operand reads per MMA, and the half-size
 // K chunk keeps a 4-deep pipeline inside 192 KiB.  All three land near 1.3 ms for the GEMM itself
 // (~1285 TF/s of issued bf16 MMA, ~0.89 of the power-capped cuBLAS rate).
+// clusters of two CTAs with TMA multicast of the database tile (only with BN=128; IBL_GEMM_MC=0 disables)
+static bool gemm_mc() {
+  static int mc = -1;
+  if (mc < 0) { const char* v = getenv("IBL_GEMM_MC"); mc = (v && atoi(v) == 0) ? 0 : 1; }
+  return mc != 0;
+}
+
 static int dist_bn() {
   static int bn = 0;
   if (!bn) { const char* v = getenv("IBL_DIST_BN"); bn = (v && atoi(v) == 128) ? 128 : 256; }
