@@ -139,6 +139,8 @@ int launch_pca_l2(const float* v, int N, int D, const float* W, const float* b, 
 int launch_l2_normalize_rows(const float* x, int N, int D, float* out, cudaStream_t s);
 int launch_row_sqnorm(const float* x, int N, int D, float* out, cudaStream_t s);
 int launch_scale(const float* x, float s, int n, float* y, cudaStream_t st);
+int launch_planes_sqnorm(const float* x, int N, int D, __nv_bfloat16* hi, __nv_bfloat16* lo, float* sq,
+                         cudaStream_t st);
 int launch_l2dist_dense(const float* q, const float* qn, int m, const float* db, const float* dbn,
                         int n, int d, float* out, long long ld_out, cudaStream_t s);
 

@@ -625,15 +625,14 @@ int ibl_l2dist_topk(ibl_engine* e, const float* q, int m, const float* db, int n
     cudaStream_t s = S(stream);
     IBL_RET(e->qn.ensure((size_t)m * sizeof(float)));
     IBL_RET(e->dbn.ensure((size_t)n * sizeof(float)));
-    IBL_RET(launch_row_sqnorm(q, m, d, e->qn.as<float>(), s));
-    IBL_RET(launch_row_sqnorm(db, n, d, e->dbn.as<float>(), s));
     const size_t qe = (size_t)m * d, de = (size_t)n * d;
     IBL_RET(e->q_pl.ensure(qe * 4));
     IBL_RET(e->db_pl.ensure(de * 4));
     __nv_bfloat16 *qh = e->q_pl.as<__nv_bfloat16>(), *dh = e->db_pl.as<__nv_bfloat16>();
-    IBL_RET(launch_f32_to_planes(q, qe, qh, qh + qe, s));
-    IBL_RET(launch_f32_to_planes(db, de, dh, dh + de, s));
-    e->launches += 4;
+    // one pass per matrix: bf16 hi/lo planes for the tensor-core GEMM + exact fp32 squared norms
+    IBL_RET(launch_planes_sqnorm(q, m, d, qh, qh + qe, e->qn.as<float>(), s));
+    IBL_RET(launch_planes_sqnorm(db, n, d, dh, dh + de, e->dbn.as<float>(), s));
+    e->launches += 2;
     const int kc = 16;                           // candidates kept per query before exact re-scoring
     if (k <= 12) {
       const int max_runs = dist_top16_max_runs(m, n_valid);
