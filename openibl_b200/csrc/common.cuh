@@ -101,6 +101,11 @@ int launch_dist_top16_tc(const __nv_bfloat16* q_hi, const __nv_bfloat16* q_lo, c
 int launch_dist_dense_tc(const __nv_bfloat16* q_hi, const __nv_bfloat16* q_lo, const float* qn, int m,
                          const __nv_bfloat16* d_hi, const __nv_bfloat16* d_lo, const float* dn, int n, int K,
                          float* out, long long ld_out, cudaStream_t s);
+// tc_gemm2.cu  (same contract on SM pairs: tcgen05.mma.cta_group::2, 256-row tiles)
+int dist_top16_2sm_max_runs(int m, int n_valid);
+int launch_dist_top16_2sm(const __nv_bfloat16* q_hi, const __nv_bfloat16* q_lo, const float* qn, int m,
+                          const __nv_bfloat16* d_hi, const __nv_bfloat16* d_lo, const float* dn, int n,
+                          int n_valid, int K, float* cand_d, long long* cand_i, int* runs_out, cudaStream_t s);
 int pca_tc_splits(int P, int D);
 int launch_pca_partial_tc(const __nv_bfloat16* w_hi, const __nv_bfloat16* w_lo, int P,
                           const __nv_bfloat16* v_hi, const __nv_bfloat16* v_lo, int N, int D,

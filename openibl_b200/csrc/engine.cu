@@ -635,13 +635,22 @@ int ibl_l2dist_topk(ibl_engine* e, const float* q, int m, const float* db, int n
     e->launches += 2;
     const int kc = 16;                           // candidates kept per query before exact re-scoring
     if (k <= 12) {
-      const int max_runs = dist_top16_max_runs(m, n_valid);
+      // SM pairs (tcgen05.mma.cta_group::2, tc_gemm2.cu) unless there is a single 128-query tile; IBL_DIST_2SM=0
+      // selects the one-SM kernel of tc_gemm.cu
+      static const bool two_sm_env = [] { const char* v = getenv("IBL_DIST_2SM"); return !v || atoi(v) != 0; }();
+      const bool two_sm = two_sm_env && m > 128;
+      const int max_runs = two_sm ? dist_top16_2sm_max_runs(m, n_valid) : dist_top16_max_runs(m, n_valid);
       IBL_RET(e->cand_d.ensure((size_t)max_runs * m * kc * sizeof(float)));
       IBL_RET(e->cand_i.ensure((size_t)max_runs * m * kc * sizeof(int64_t)));
       int runs = 0;
-      IBL_RET(launch_dist_top16_tc(qh, qh + qe, e->qn.as<float>(), m, dh, dh + de, e->dbn.as<float>(), n,
-                                   n_valid, d, e->cand_d.as<float>(), e->cand_i.as<long long>(), max_runs,
-                                   &runs, s));
+      if (two_sm) {
+        IBL_RET(launch_dist_top16_2sm(qh, qh + qe, e->qn.as<float>(), m, dh, dh + de, e->dbn.as<float>(), n,
+                                      n_valid, d, e->cand_d.as<float>(), e->cand_i.as<long long>(), &runs, s));
+      } else {
+        IBL_RET(launch_dist_top16_tc(qh, qh + qe, e->qn.as<float>(), m, dh, dh + de, e->dbn.as<float>(), n,
+                                     n_valid, d, e->cand_d.as<float>(), e->cand_i.as<long long>(), max_runs,
+                                     &runs, s));
+      }
       e->launches++;
       const long long* ci = e->cand_i.as<long long>();
       if (runs > 1) {

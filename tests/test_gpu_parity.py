@@ -179,6 +179,32 @@ def test_sharp_netvlad_full_chain_vs_oracle(eng, O):
     assert float(d[~torch.eye(6, dtype=torch.bool)].min()) > 1e-3
 
 
+def test_shapes_tokyo_like_and_microbatching(eng, O):
+    """Tokyo 24/7 queries arrive one at a time with arbitrary sizes (examples/test.py:44-48: batch 1,
+    Resize(max(h,w))); large batches are split into micro-batches of 32 inside ibl_extract; the host entry
+    point splits a batch >= 16 into two parts to overlap the copy.  All against the oracle."""
+    sd = synth.make_state_dict(seed=17, sharp=True, with_pca=True, pca_dim=256, bias_scale=0.02)
+    _bind(eng, sd)
+    for (n, h, w) in ((1, 112, 80), (1, 83, 131), (3, 48, 208)):
+        x = synth.make_images(seed=31 + h, batch=n, height=h, width=w)
+        with torch.no_grad():
+            want = O.embednetpca_forward(x, sd)
+        got, _ = eng.extract(x.cuda(), pca=True)
+        assert got.shape == want.shape
+        assert rel_l2(got.cpu(), want) < DESC_TOL, (n, h, w, rel_l2(got.cpu(), want))
+    x = synth.make_images(seed=40, batch=37, height=32, width=48)          # 32 + 5 micro-batches
+    with torch.no_grad():
+        want = O.embednetpca_forward(x, sd)
+    got, pool = eng.extract(x.cuda(), pca=True, want_pool=True)
+    assert rel_l2(got.cpu(), want) < DESC_TOL and tuple(pool.shape) == (37, 512)
+    out_host = torch.empty(37, 256).pin_memory()
+    eng.extract_host(x.pin_memory(), out_host, pca=True)                    # 9 + 28 split with overlapped copy
+    assert torch.equal(out_host, got.cpu())
+    out_host2 = torch.empty(37, 256)                                        # pageable host memory also works
+    eng.extract_host(x, out_host2, pca=True)
+    assert torch.equal(out_host2, got.cpu())
+
+
 def test_models_api_drop_in(eng):
     """The nn.Module mirror (what examples/test.py builds, :58-70) gives the golden outputs."""
     from ibl import models
