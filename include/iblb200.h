@@ -178,6 +178,12 @@ int ibl_debug_conv3x3(ibl_engine* e, const float* x_nhwc, int N, int H, int W, i
 /* MN-major tcgen05 operand self-test: C[128,64] = A^T B for A [128 k,128 m], B [128 k,64 n] (fp32, device),
  * bf16x3 on the tensor core.  Synchronises. */
 int ibl_debug_gemm_tn(ibl_engine* e, const float* A, const float* B, float* C, void* stream);
+/* Hardware probe (tools/probe_umma_stride.py): D[128,64] = view(A) . B^T on tcgen05 where view row m is row
+ * s0 + (m/8)*group_rows + (m%8) of the TMA-staged, 128B-swizzled [rows][64] bf16 tile A; base_mode 1 sets the
+ * descriptor's base_offset field to the start row's swizzle phase.  Decides whether a conv can read its nine
+ * taps out of one halo tile. */
+int ibl_debug_umma_strided(ibl_engine* e, const void* A, int rows, const void* B, int s0, int group_rows,
+                           int base_mode, float* D, void* stream);
 /* Average device time (ms) of one backbone layer over `reps` launches, weights from the engine
  * (tools/bench_layers.py).  layer 0 = conv1_1 (x NCHW [N,3,H,W]); 1..12 = conv1_2..conv5_3
  * (x NHWC [N,H,W,Cin] fp32).  Synchronises. */

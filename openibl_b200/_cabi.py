@@ -48,6 +48,7 @@ SIGNATURES = {
     "ibl_l2dist_topk_host": (c_int, [_P, _P, c_int, _P, c_int, c_int, c_int, _P, _P, _P]),
     "ibl_selftest_tc": (c_int, [_P, POINTER(c_float)]),
     "ibl_debug_gemm_tn": (c_int, [_P, _P, _P, _P, _P]),
+    "ibl_debug_umma_strided": (c_int, [_P, _P, c_int, _P, c_int, c_int, c_int, _P, _P]),
     "ibl_debug_time_layer": (c_int, [_P, c_int, _P, c_int, c_int, c_int, c_int, c_int, POINTER(c_float)]),
     "ibl_debug_conv3x3": (c_int, [_P, _P, c_int, c_int, c_int, c_int, _P, _P, c_int, c_int, c_int, c_int,
                                   c_int, _P, _P]),

@@ -85,6 +85,9 @@ int launch_conv1_1_tc(const float* x_nchw, const float* w_oihw, const float* bia
 // tc_netvlad.cu
 int debug_gemm_tn(const float* A, const float* B, float* C, cudaStream_t s);
 int netvlad_tc_units(int B, int S);
+// tc_probe.cu
+int debug_umma_strided(const void* A, int rows, const void* B, int s0, int group_rows, int base_mode, float* D,
+                       cudaStream_t s);
 int launch_netvlad_tc(const __nv_bfloat16* x_hi, const __nv_bfloat16* x_lo, int B, int S,
                       const __nv_bfloat16* w_hi, const __nv_bfloat16* w_lo, const float* ssq, int ssq_parts,
                       const float* cent, bool normalize_input, float* part, float* asum_part,

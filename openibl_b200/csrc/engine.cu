@@ -845,6 +845,14 @@ int ibl_debug_gemm_tn(ibl_engine* e, const float* A, const float* B, float* C, v
   return debug_gemm_tn(A, B, C, S(stream));
 }
 
+int ibl_debug_umma_strided(ibl_engine* e, const void* A, int rows, const void* B, int s0, int group_rows,
+                            int base_mode, float* D, void* stream) {
+  IBL_REQUIRE(e && A && B && D, "null argument");
+  DeviceGuard g(e->device);
+  e->launches += 1;
+  return debug_umma_strided(A, rows, B, s0, group_rows, base_mode, D, S(stream));
+}
+
 // Timing hooks (tools/bench_layers.py): average device time of one backbone layer over `reps`
 // back-to-back launches, weights taken from the engine (ibl_engine_set_vgg16).  layer 0 = conv1_1
 // (x is NCHW [N,3,H,W]); layers 1..12 take x NHWC [N,H,W,Cin] fp32 (converted to planes once).

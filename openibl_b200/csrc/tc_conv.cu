@@ -94,9 +94,12 @@ constexpr int TC_BM = 128;
 constexpr int TC_BK = 64;                       // bf16 elements per K-chunk = one 128-byte row
 constexpr int TC_A_BYTES = TC_BM * TC_BK * 2;   // 16 KiB per plane
 
-template <int BN>
+// PAIR: the CTA is one half of an SM pair (tcgen05.mma.cta_group::2, 256-pixel M tile): it stages its own
+// 128-pixel patch and HALF of the BN-wide weight tile; per stage and SM the TMA fill drops from 96 to 64 KiB
+// (BN = 256) and the tensor core reads half of B from the peer's shared memory.
+template <int BN, bool PAIR = false>
 struct ConvTcSmem {
-  static constexpr int B_BYTES = BN * TC_BK * 2;
+  static constexpr int B_BYTES = (PAIR ? BN / 2 : BN) * TC_BK * 2;
   static constexpr int STAGE_BYTES = 2 * TC_A_BYTES + 2 * B_BYTES;
 };
 
@@ -105,7 +108,7 @@ __device__ __forceinline__ uint32_t pack_bf16x2(float a, float b) {
   return *reinterpret_cast<uint32_t*>(&t);
 }
 
-template <int BN, int STAGES>
+template <int BN, int STAGES, bool PAIR>
 __global__ void __launch_bounds__(192, 1)
 conv3x3_tc_kernel(const __grid_constant__ CUtensorMap tm_xhi, const __grid_constant__ CUtensorMap tm_xlo,
                   const __grid_constant__ CUtensorMap tm_whi, const __grid_constant__ CUtensorMap tm_wlo,
@@ -113,8 +116,14 @@ conv3x3_tc_kernel(const __grid_constant__ CUtensorMap tm_xhi, const __grid_const
   extern __shared__ __align__(1024) uint8_t smem_raw[];
   // 1024-byte alignment is required by the 128B swizzle; dynamic smem base is only 16B-aligned
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
-  constexpr int B_BYTES = ConvTcSmem<BN>::B_BYTES;
-  constexpr int STAGE_BYTES = ConvTcSmem<BN>::STAGE_BYTES;
+  constexpr int B_BYTES = ConvTcSmem<BN, PAIR>::B_BYTES;
+  constexpr int STAGE_BYTES = ConvTcSmem<BN, PAIR>::STAGE_BYTES;
+  static_assert(!(PAIR && BN == 64), "the pair variant is for BN = 128 / 256");
+  const uint32_t rank = PAIR ? cluster_ctarank() : 0u;
+  const bool leader = rank == 0;
+  // pair mode: the two CTAs of a cluster share one work item = (two adjacent patches, one N tile)
+  const int worker = PAIR ? (int)(blockIdx.x >> 1) : (int)blockIdx.x;
+  const int n_workers = PAIR ? (int)(gridDim.x >> 1) : (int)gridDim.x;
   uint64_t* bars = reinterpret_cast<uint64_t*>(smem + STAGES * STAGE_BYTES);
   uint64_t* full_bar = bars;
   uint64_t* empty_bar = bars + STAGES;
@@ -138,22 +147,27 @@ conv3x3_tc_kernel(const __grid_constant__ CUtensorMap tm_xhi, const __grid_const
     tma_prefetch_desc(&tm_whi);
     tma_prefetch_desc(&tm_wlo);
     for (int i = 0; i < STAGES; ++i) {
-      mbar_init(&full_bar[i], 1);
+      mbar_init(&full_bar[i], PAIR ? 2 : 1);    // pair: leader's expect_tx + the peer producer's arrive
       mbar_init(&empty_bar[i], 1);
     }
     mbar_init(&tfull_bar[0], 1);
     mbar_init(&tfull_bar[1], 1);
-    mbar_init(&tempty_bar[0], 4);
-    mbar_init(&tempty_bar[1], 4);
+    mbar_init(&tempty_bar[0], PAIR ? 8 : 4);    // pair: the epilogue warps of both CTAs (leader's barrier)
+    mbar_init(&tempty_bar[1], PAIR ? 8 : 4);
     fence_barrier_init();
     fence_proxy_async();
   }
   if (warp == 1) {
-    tmem_alloc(tmem_slot, TMEM_COLS);
-    tmem_relinquish();
+    if (PAIR) {
+      tmem_alloc_2sm(tmem_slot, TMEM_COLS);
+    } else {
+      tmem_alloc(tmem_slot, TMEM_COLS);
+      tmem_relinquish();
+    }
   }
   tc_fence_before();
   __syncthreads();
+  if (PAIR) cluster_sync_all();
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
 
@@ -167,37 +181,47 @@ conv3x3_tc_kernel(const __grid_constant__ CUtensorMap tm_xhi, const __grid_const
     if (lane == 0) {
       int stage = 0;
       uint32_t phase = 0;
-      for (int tile = blockIdx.x; tile < a.total_tiles; tile += gridDim.x) {
+      for (int tile = worker; tile < a.total_tiles; tile += n_workers) {
         const int nt = tile % a.n_tiles;
-        const int pt = tile / a.n_tiles;
-        const int img = pt / tiles_per_img;
-        const int rem = pt - img * tiles_per_img;
+        const int pt = PAIR ? 2 * (tile / a.n_tiles) + (int)rank : tile / a.n_tiles;
+        const int img = pt / tiles_per_img;     // pair: an odd patch count leaves img == N for the last
+        const int rem = pt - img * tiles_per_img;   // peer: TMA zero-fills, the epilogue stores nothing
         const int h0 = (rem / a.tiles_w) * (TC_BM >> a.tw_log2);
         const int w0 = (rem % a.tiles_w) * TW;
-        const int n0 = nt * BN;
+        const int n0 = PAIR ? nt * BN + (int)rank * (BN / 2) : nt * BN;
         for (int kit = 0; kit < kiters; ++kit) {
           const int tap = kit / kchunks;
           const int c0 = (kit - tap * kchunks) * TC_BK;
           const int kh = tap / 3 - 1, kw = tap % 3 - 1;
           mbar_wait(&empty_bar[stage], phase ^ 1);
           uint8_t* st = smem + stage * STAGE_BYTES;
-          mbar_arrive_expect_tx(&full_bar[stage], STAGE_BYTES);
-          tma_load_4d(st, &tm_xhi, &full_bar[stage], c0, w0 + kw, h0 + kh, img);
-          tma_load_4d(st + TC_A_BYTES, &tm_xlo, &full_bar[stage], c0, w0 + kw, h0 + kh, img);
-          tma_load_3d(st + 2 * TC_A_BYTES, &tm_whi, &full_bar[stage], c0, n0, tap);
-          tma_load_3d(st + 2 * TC_A_BYTES + B_BYTES, &tm_wlo, &full_bar[stage], c0, n0, tap);
+          if (PAIR) {
+            const uint32_t lead_full = mapa_u32(smem_u32(&full_bar[stage]), 0);
+            if (leader) mbar_arrive_expect_tx(&full_bar[stage], 2 * STAGE_BYTES);   // bytes of both CTAs
+            else mbar_arrive_remote(lead_full);
+            tma_load_4d_2sm(st, &tm_xhi, lead_full, c0, w0 + kw, h0 + kh, img);
+            tma_load_4d_2sm(st + TC_A_BYTES, &tm_xlo, lead_full, c0, w0 + kw, h0 + kh, img);
+            tma_load_3d_2sm(st + 2 * TC_A_BYTES, &tm_whi, lead_full, c0, n0, tap);
+            tma_load_3d_2sm(st + 2 * TC_A_BYTES + B_BYTES, &tm_wlo, lead_full, c0, n0, tap);
+          } else {
+            mbar_arrive_expect_tx(&full_bar[stage], STAGE_BYTES);
+            tma_load_4d(st, &tm_xhi, &full_bar[stage], c0, w0 + kw, h0 + kh, img);
+            tma_load_4d(st + TC_A_BYTES, &tm_xlo, &full_bar[stage], c0, w0 + kw, h0 + kh, img);
+            tma_load_3d(st + 2 * TC_A_BYTES, &tm_whi, &full_bar[stage], c0, n0, tap);
+            tma_load_3d(st + 2 * TC_A_BYTES + B_BYTES, &tm_wlo, &full_bar[stage], c0, n0, tap);
+          }
           if (++stage == STAGES) { stage = 0; phase ^= 1; }
         }
       }
     }
   } else if (warp == 1) {
     // ================= MMA issuer =================
-    if (lane == 0) {
-      constexpr uint32_t idesc = umma_idesc_bf16_f32(TC_BM, BN);
+    if (lane == 0 && leader) {
+      constexpr uint32_t idesc = umma_idesc_bf16_f32(PAIR ? 2 * TC_BM : TC_BM, BN);
       int stage = 0;
       uint32_t phase = 0;
       int it = 0;
-      for (int tile = blockIdx.x; tile < a.total_tiles; tile += gridDim.x, ++it) {
+      for (int tile = worker; tile < a.total_tiles; tile += n_workers, ++it) {
         const int as = it & 1;
         const uint32_t aphase = (it >> 1) & 1;
         mbar_wait(&tempty_bar[as], aphase ^ 1);
@@ -220,16 +244,24 @@ conv3x3_tc_kernel(const __grid_constant__ CUtensorMap tm_xhi, const __grid_const
               constexpr uint32_t idesc2n = umma_idesc_bf16_f32(TC_BM, 2 * BN);
               umma_bf16(d_tmem, a_hi + ko, b_hi + ko, idesc2n, first);          // [hi.hi | hi.lo]
               umma_bf16(d_tmem + 2 * BN, a_lo + ko, b_hi + ko, idesc, first);   // lo.hi
+            } else if (PAIR) {
+              umma_bf16_2sm(d_tmem, a_lo + ko, b_hi + ko, idesc, first);
+              umma_bf16_2sm(d_tmem, a_hi + ko, b_lo + ko, idesc, 1u);
+              umma_bf16_2sm(d_tmem, a_hi + ko, b_hi + ko, idesc, 1u);
             } else {
               umma_bf16(d_tmem, a_lo + ko, b_hi + ko, idesc, first);
               umma_bf16(d_tmem, a_hi + ko, b_lo + ko, idesc, 1u);
               umma_bf16(d_tmem, a_hi + ko, b_hi + ko, idesc, 1u);
             }
           }
-          umma_commit(&empty_bar[stage]);   // frees the smem slot when these MMAs retire
+          // frees the smem slot (in both CTAs of a pair) when these MMAs retire
+          if (PAIR) umma_commit_2sm_mc(&empty_bar[stage], 0x3);
+          else umma_commit(&empty_bar[stage]);
           if (++stage == STAGES) { stage = 0; phase ^= 1; }
         }
-        umma_commit(&tfull_bar[as]);        // accumulator ready for the epilogue
+        // accumulator ready for the epilogue
+        if (PAIR) umma_commit_2sm_mc(&tfull_bar[as], 0x3);
+        else umma_commit(&tfull_bar[as]);
       }
     }
   } else {
@@ -238,11 +270,11 @@ conv3x3_tc_kernel(const __grid_constant__ CUtensorMap tm_xhi, const __grid_const
     const int m = q * 32 + lane;            // accumulator row = pixel index inside the patch
     const int r = m >> a.tw_log2, c = m & (TW - 1);
     int it = 0;
-    for (int tile = blockIdx.x; tile < a.total_tiles; tile += gridDim.x, ++it) {
+    for (int tile = worker; tile < a.total_tiles; tile += n_workers, ++it) {
       const int as = it & 1;
       const uint32_t aphase = (it >> 1) & 1;
       const int nt = tile % a.n_tiles;
-      const int pt = tile / a.n_tiles;
+      const int pt = PAIR ? 2 * (tile / a.n_tiles) + (int)rank : tile / a.n_tiles;
       const int img = pt / tiles_per_img;
       const int rem = pt - img * tiles_per_img;
       const int h0 = (rem / a.tiles_w) * (TC_BM >> a.tw_log2);
@@ -254,10 +286,10 @@ conv3x3_tc_kernel(const __grid_constant__ CUtensorMap tm_xhi, const __grid_const
       if (a.pool) {
         const int OH = a.H >> 1, OW = a.W >> 1;
         const int oh = h >> 1, ow = w >> 1;
-        valid = ((r & 1) == 0) && ((c & 1) == 0) && oh < OH && ow < OW;
+        valid = ((r & 1) == 0) && ((c & 1) == 0) && oh < OH && ow < OW && img < a.N;
         pix = ((long long)img * OH + oh) * OW + ow;
       } else {
-        valid = h < a.H && w < a.W;
+        valid = h < a.H && w < a.W && img < a.N;
         pix = ((long long)img * a.H + h) * a.W + w;
       }
       mbar_wait(&tfull_bar[as], aphase);
@@ -332,34 +364,56 @@ conv3x3_tc_kernel(const __grid_constant__ CUtensorMap tm_xhi, const __grid_const
       if (a.ssq && valid && !a.pool) a.ssq[(long long)nt * a.ssq_stride + pix] = ssq_acc;
       tc_fence_before();
       __syncwarp();
-      if (lane == 0) mbar_arrive(&tempty_bar[as]);
+      if (lane == 0) {
+        if (PAIR && !leader) mbar_arrive_remote(mapa_u32(smem_u32(&tempty_bar[as]), 0));
+        else mbar_arrive(&tempty_bar[as]);
+      }
     }
   }
 
   tc_fence_before();
   __syncthreads();
+  if (PAIR) cluster_sync_all();
   if (warp == 1) {
     tc_fence_after();
-    tmem_dealloc(tmem_base, TMEM_COLS);
+    if (PAIR) tmem_dealloc_2sm(tmem_base, TMEM_COLS);
+    else tmem_dealloc(tmem_base, TMEM_COLS);
   }
 }
 
 // ---- host launcher --------------------------------------------------------------------------
-template <int BN, int STAGES>
+template <int BN, int STAGES, bool PAIR>
 static int launch_tc_variant(const CUtensorMap& xhi, const CUtensorMap& xlo, const CUtensorMap& whi,
                              const CUtensorMap& wlo, const ConvTcArgs& a, cudaStream_t s) {
-  constexpr int smem = STAGES * ConvTcSmem<BN>::STAGE_BYTES + 1024 /*align slack*/ + 256 /*barriers*/;
+  constexpr int smem = STAGES * ConvTcSmem<BN, PAIR>::STAGE_BYTES + 1024 /*align slack*/ + 256 /*barriers*/;
   static bool attr_done = false;
   if (!attr_done) {
-    IBL_CUDA_OK(cudaFuncSetAttribute(conv3x3_tc_kernel<BN, STAGES>,
+    IBL_CUDA_OK(cudaFuncSetAttribute(conv3x3_tc_kernel<BN, STAGES, PAIR>,
                                      cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
     attr_done = true;
   }
   int dev = 0, sms = 148;
   cudaGetDevice(&dev);
   cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+  if (PAIR) {   // a.total_tiles counts pair work items; one 2-CTA cluster per item, at most sms/2 clusters
+    const int pairs = a.total_tiles < sms / 2 ? a.total_tiles : sms / 2;
+    cudaLaunchConfig_t cfg{};
+    cfg.gridDim = dim3(2 * pairs);
+    cfg.blockDim = dim3(192);
+    cfg.dynamicSmemBytes = smem;
+    cfg.stream = s;
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeClusterDimension;
+    attr[0].val.clusterDim.x = 2;
+    attr[0].val.clusterDim.y = 1;
+    attr[0].val.clusterDim.z = 1;
+    cfg.attrs = attr;
+    cfg.numAttrs = 1;
+    IBL_CUDA_OK(cudaLaunchKernelEx(&cfg, conv3x3_tc_kernel<BN, STAGES, PAIR>, xhi, xlo, whi, wlo, a));
+    return IBL_OK;
+  }
   int grid = a.total_tiles < sms ? a.total_tiles : sms;
-  conv3x3_tc_kernel<BN, STAGES><<<grid, 192, smem, s>>>(xhi, xlo, whi, wlo, a);
+  conv3x3_tc_kernel<BN, STAGES, PAIR><<<grid, 192, smem, s>>>(xhi, xlo, whi, wlo, a);
   IBL_CUDA_OK(cudaGetLastError());
   return IBL_OK;
 }
@@ -396,8 +450,14 @@ int launch_conv3x3_tc(const __nv_bfloat16* x_hi, const __nv_bfloat16* x_lo, cons
     if (env_bn < 0) { const char* v = getenv("IBL_TC_BN"); env_bn = v ? atoi(v) : 0; }
     if (env_bn > 0 && !g_tc_bn_override && cout % env_bn == 0) bn = env_bn;
   }
+  // SM pairs for the 256-wide tiles (measured 3-7 % faster on conv4_x/conv5_x, neutral on conv3_x; the
+  // 128-wide pair variant is 30 % SLOWER than one SM per tile and is only reachable with IBL_CONV_2SM=2).
+  // IBL_CONV_2SM=0: one-SM kernels everywhere.
+  static const int pair_env = [] { const char* v = getenv("IBL_CONV_2SM"); return v ? atoi(v) : 1; }();
+  const long long patches = (long long)N * a.tiles_h * a.tiles_w;
+  const bool pair = pair_env && patches >= 2 && (bn == 256 || (bn == 128 && pair_env == 2));
   a.n_tiles = cout / bn;
-  a.total_tiles = N * a.tiles_h * a.tiles_w * a.n_tiles;
+  a.total_tiles = (int)((pair ? (patches + 1) / 2 : patches) * a.n_tiles);
   a.relu = relu; a.pool = pool;
   a.bias = p.bias; a.y_hi = y_hi; a.y_lo = y_lo; a.y_f32 = y_f32;
   a.ssq = pool ? nullptr : ssq;
@@ -415,13 +475,17 @@ int launch_conv3x3_tc(const __nv_bfloat16* x_hi, const __nv_bfloat16* x_lo, cons
   {
     uint64_t dims[3] = {(uint64_t)cin, (uint64_t)cout, 9};
     uint64_t str[2] = {(uint64_t)cin * 2, (uint64_t)cout * cin * 2};
-    uint32_t box[3] = {64, (uint32_t)bn, 1};
+    uint32_t box[3] = {64, (uint32_t)(pair ? bn / 2 : bn), 1};
     IBL_RET(make_tmap(&m_whi, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 3, p.w_hi, dims, str, box));
     IBL_RET(make_tmap(&m_wlo, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 3, p.w_lo, dims, str, box));
   }
-  if (bn == 64) return launch_tc_variant<64, 4>(m_xhi, m_xlo, m_whi, m_wlo, a, s);
-  if (bn == 128) return launch_tc_variant<128, 3>(m_xhi, m_xlo, m_whi, m_wlo, a, s);
-  return launch_tc_variant<256, 2>(m_xhi, m_xlo, m_whi, m_wlo, a, s);
+  if (bn == 64) return launch_tc_variant<64, 4, false>(m_xhi, m_xlo, m_whi, m_wlo, a, s);
+  if (bn == 128) {
+    if (pair) return launch_tc_variant<128, 4, true>(m_xhi, m_xlo, m_whi, m_wlo, a, s);
+    return launch_tc_variant<128, 3, false>(m_xhi, m_xlo, m_whi, m_wlo, a, s);
+  }
+  if (pair) return launch_tc_variant<256, 3, true>(m_xhi, m_xlo, m_whi, m_wlo, a, s);
+  return launch_tc_variant<256, 2, false>(m_xhi, m_xlo, m_whi, m_wlo, a, s);
 }
 
 // ---- 2x2 max-pool on hi/lo planes (used only when the conv epilogue did not pool) -------------
