@@ -97,10 +97,22 @@ constexpr int TC_A_BYTES = TC_BM * TC_BK * 2;   // 16 KiB per plane
 // PAIR: the CTA is one half of an SM pair (tcgen05.mma.cta_group::2, 256-pixel M tile): it stages its own
 // 128-pixel patch and HALF of the BN-wide weight tile; per stage and SM the TMA fill drops from 96 to 64 KiB
 // (BN = 256) and the tensor core reads half of B from the peer's shared memory.
-template <int BN, bool PAIR = false>
+//
+// HALO: instead of one [128 px][64 ch] im2col box per tap, the producer stages ONE halo tile per 64-channel
+// chunk -- the (16+2) x (8+2) pixel neighbourhood of a 16x8 patch, 180 rows of 128 B per plane -- and the
+// nine taps are nine views of it: tap (kh,kw) starts (kh*10 + kw) rows into the tile and consecutive 8-pixel
+// row groups are 10 rows (1280 B) apart.  The 128B swizzle is a pure function of the shared-memory address,
+// so a descriptor whose start is only 128-byte aligned and whose group stride is not a multiple of 1024 B
+// reads the TMA-written tile correctly (probed on hardware: tc_probe.cu / tools/probe_umma_stride.py).
+// L2->SM traffic of the A operand drops from 9 x 32 KiB to 45 KiB per chunk; the weights get their own ring.
+constexpr int TC_HALO_W = 10, TC_HALO_H = 18;
+constexpr int TC_HALO_PLANE = 23 * 1024;        // 180 rows x 128 B = 23040 B, padded to the swizzle period
+constexpr int TC_HALO_STAGE = 2 * TC_HALO_PLANE;
+template <int BN, bool PAIR = false, bool HALO = false, int NA = 0>
 struct ConvTcSmem {
   static constexpr int B_BYTES = (PAIR ? BN / 2 : BN) * TC_BK * 2;
-  static constexpr int STAGE_BYTES = 2 * TC_A_BYTES + 2 * B_BYTES;
+  static constexpr int STAGE_BYTES = HALO ? 2 * B_BYTES : 2 * TC_A_BYTES + 2 * B_BYTES;
+  static constexpr int A_RING = HALO ? NA * TC_HALO_STAGE : 0;
 };
 
 __device__ __forceinline__ uint32_t pack_bf16x2(float a, float b) {
@@ -108,7 +120,7 @@ __device__ __forceinline__ uint32_t pack_bf16x2(float a, float b) {
   return *reinterpret_cast<uint32_t*>(&t);
 }
 
-template <int BN, int STAGES, bool PAIR>
+template <int BN, int STAGES, bool PAIR, bool HALO, int NA>
 __global__ void __launch_bounds__(192, 1)
 conv3x3_tc_kernel(const __grid_constant__ CUtensorMap tm_xhi, const __grid_constant__ CUtensorMap tm_xlo,
                   const __grid_constant__ CUtensorMap tm_whi, const __grid_constant__ CUtensorMap tm_wlo,
@@ -116,20 +128,24 @@ conv3x3_tc_kernel(const __grid_constant__ CUtensorMap tm_xhi, const __grid_const
   extern __shared__ __align__(1024) uint8_t smem_raw[];
   // 1024-byte alignment is required by the 128B swizzle; dynamic smem base is only 16B-aligned
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
-  constexpr int B_BYTES = ConvTcSmem<BN, PAIR>::B_BYTES;
-  constexpr int STAGE_BYTES = ConvTcSmem<BN, PAIR>::STAGE_BYTES;
+  constexpr int B_BYTES = ConvTcSmem<BN, PAIR, HALO, NA>::B_BYTES;
+  constexpr int STAGE_BYTES = ConvTcSmem<BN, PAIR, HALO, NA>::STAGE_BYTES;
+  constexpr int A_RING = ConvTcSmem<BN, PAIR, HALO, NA>::A_RING;
+  uint8_t* ring = smem + A_RING;              // HALO: the halo ring sits in front of the weight ring
   static_assert(!(PAIR && BN == 64), "the pair variant is for BN = 128 / 256");
   const uint32_t rank = PAIR ? cluster_ctarank() : 0u;
   const bool leader = rank == 0;
   // pair mode: the two CTAs of a cluster share one work item = (two adjacent patches, one N tile)
   const int worker = PAIR ? (int)(blockIdx.x >> 1) : (int)blockIdx.x;
   const int n_workers = PAIR ? (int)(gridDim.x >> 1) : (int)gridDim.x;
-  uint64_t* bars = reinterpret_cast<uint64_t*>(smem + STAGES * STAGE_BYTES);
+  uint64_t* bars = reinterpret_cast<uint64_t*>(ring + STAGES * STAGE_BYTES);
   uint64_t* full_bar = bars;
   uint64_t* empty_bar = bars + STAGES;
   uint64_t* tfull_bar = bars + 2 * STAGES;
   uint64_t* tempty_bar = bars + 2 * STAGES + 2;
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 2 * STAGES + 4);
+  uint64_t* afull_bar = bars + 2 * STAGES + 5;          // HALO only: [NA] + [NA]
+  uint64_t* aempty_bar = afull_bar + NA;
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   // BN = 64 (conv1_2): an M=128,N=64 MMA is bound by the 4 KiB shared-memory read of its A operand
@@ -149,6 +165,10 @@ conv3x3_tc_kernel(const __grid_constant__ CUtensorMap tm_xhi, const __grid_const
     for (int i = 0; i < STAGES; ++i) {
       mbar_init(&full_bar[i], PAIR ? 2 : 1);    // pair: leader's expect_tx + the peer producer's arrive
       mbar_init(&empty_bar[i], 1);
+    }
+    for (int i = 0; i < NA; ++i) {
+      mbar_init(&afull_bar[i], PAIR ? 2 : 1);
+      mbar_init(&aempty_bar[i], 1);
     }
     mbar_init(&tfull_bar[0], 1);
     mbar_init(&tfull_bar[1], 1);
@@ -179,8 +199,67 @@ conv3x3_tc_kernel(const __grid_constant__ CUtensorMap tm_xhi, const __grid_const
   if (warp == 0) {
     // ================= TMA producer =================
     if (lane == 0) {
-      int stage = 0;
-      uint32_t phase = 0;
+      int stage = 0, astage = 0;
+      uint32_t phase = 0, aphase = 0;
+      (void)astage; (void)aphase;
+      if constexpr (HALO) {
+        // Two independent streams -- halo tiles (one per tile and 64-channel chunk) and weight taps (nine per
+        // halo) -- each issued as soon as its ring has a free slot, so the halo of the NEXT chunk is in flight
+        // while the taps of the current one are still being fed.
+        auto coords = [&](int tile, int& img, int& h0, int& w0, int& n0) {
+          const int nt = tile % a.n_tiles;
+          const int pt = PAIR ? 2 * (tile / a.n_tiles) + (int)rank : tile / a.n_tiles;
+          img = pt / tiles_per_img;             // pair: an odd patch count leaves img == N for the last peer:
+          const int rem = pt - img * tiles_per_img;   // TMA zero-fills, the epilogue stores nothing
+          h0 = (rem / a.tiles_w) * (TC_BM >> a.tw_log2);
+          w0 = (rem % a.tiles_w) * TW;
+          n0 = PAIR ? nt * BN + (int)rank * (BN / 2) : nt * BN;
+        };
+        int tA = worker, kcA = 0, tB = worker, kcB = 0, tapB = 0;
+        while (tB < a.total_tiles) {
+          if (tA < a.total_tiles && mbar_try_wait(&aempty_bar[astage], aphase ^ 1)) {
+            int img, h0, w0, n0;
+            coords(tA, img, h0, w0, n0);
+            (void)n0;
+            const int c0 = kcA * TC_BK;
+            uint8_t* sa = smem + astage * TC_HALO_STAGE;
+            constexpr uint32_t kHaloBytes = 2u * TC_HALO_W * TC_HALO_H * 128u;
+            if (PAIR) {
+              const uint32_t lead = mapa_u32(smem_u32(&afull_bar[astage]), 0);
+              if (leader) mbar_arrive_expect_tx(&afull_bar[astage], 2 * kHaloBytes);
+              else mbar_arrive_remote(lead);
+              tma_load_4d_2sm(sa, &tm_xhi, lead, c0, w0 - 1, h0 - 1, img);
+              tma_load_4d_2sm(sa + TC_HALO_PLANE, &tm_xlo, lead, c0, w0 - 1, h0 - 1, img);
+            } else {
+              mbar_arrive_expect_tx(&afull_bar[astage], kHaloBytes);
+              tma_load_4d(sa, &tm_xhi, &afull_bar[astage], c0, w0 - 1, h0 - 1, img);
+              tma_load_4d(sa + TC_HALO_PLANE, &tm_xlo, &afull_bar[astage], c0, w0 - 1, h0 - 1, img);
+            }
+            if (++astage == NA) { astage = 0; aphase ^= 1; }
+            if (++kcA == kchunks) { kcA = 0; tA += n_workers; }
+            continue;
+          }
+          if (mbar_try_wait(&empty_bar[stage], phase ^ 1)) {
+            int img, h0, w0, n0;
+            coords(tB, img, h0, w0, n0);
+            const int c0 = kcB * TC_BK;
+            uint8_t* st = ring + stage * STAGE_BYTES;
+            if (PAIR) {
+              const uint32_t lead_full = mapa_u32(smem_u32(&full_bar[stage]), 0);
+              if (leader) mbar_arrive_expect_tx(&full_bar[stage], 2 * STAGE_BYTES);
+              else mbar_arrive_remote(lead_full);
+              tma_load_3d_2sm(st, &tm_whi, lead_full, c0, n0, tapB);
+              tma_load_3d_2sm(st + B_BYTES, &tm_wlo, lead_full, c0, n0, tapB);
+            } else {
+              mbar_arrive_expect_tx(&full_bar[stage], STAGE_BYTES);
+              tma_load_3d(st, &tm_whi, &full_bar[stage], c0, n0, tapB);
+              tma_load_3d(st + B_BYTES, &tm_wlo, &full_bar[stage], c0, n0, tapB);
+            }
+            if (++stage == STAGES) { stage = 0; phase ^= 1; }
+            if (++tapB == 9) { tapB = 0; if (++kcB == kchunks) { kcB = 0; tB += n_workers; } }
+          }
+        }
+      } else {
       for (int tile = worker; tile < a.total_tiles; tile += n_workers) {
         const int nt = tile % a.n_tiles;
         const int pt = PAIR ? 2 * (tile / a.n_tiles) + (int)rank : tile / a.n_tiles;
@@ -189,6 +268,7 @@ conv3x3_tc_kernel(const __grid_constant__ CUtensorMap tm_xhi, const __grid_const
         const int h0 = (rem / a.tiles_w) * (TC_BM >> a.tw_log2);
         const int w0 = (rem % a.tiles_w) * TW;
         const int n0 = PAIR ? nt * BN + (int)rank * (BN / 2) : nt * BN;
+        {
         for (int kit = 0; kit < kiters; ++kit) {
           const int tap = kit / kchunks;
           const int c0 = (kit - tap * kchunks) * TC_BK;
@@ -212,14 +292,17 @@ conv3x3_tc_kernel(const __grid_constant__ CUtensorMap tm_xhi, const __grid_const
           }
           if (++stage == STAGES) { stage = 0; phase ^= 1; }
         }
+        }
+      }
       }
     }
   } else if (warp == 1) {
     // ================= MMA issuer =================
     if (lane == 0 && leader) {
       constexpr uint32_t idesc = umma_idesc_bf16_f32(PAIR ? 2 * TC_BM : TC_BM, BN);
-      int stage = 0;
-      uint32_t phase = 0;
+      int stage = 0, hstage = 0;
+      uint32_t phase = 0, hphase = 0;
+      (void)hstage; (void)hphase;
       int it = 0;
       for (int tile = worker; tile < a.total_tiles; tile += n_workers, ++it) {
         const int as = it & 1;
@@ -227,6 +310,50 @@ conv3x3_tc_kernel(const __grid_constant__ CUtensorMap tm_xhi, const __grid_const
         mbar_wait(&tempty_bar[as], aphase ^ 1);
         tc_fence_after();
         const uint32_t d_tmem = tmem_base + as * ACC_COLS;
+        if constexpr (HALO) {
+          // K-major SW128 view of the halo tile: 8-pixel row groups 10 rows apart
+          constexpr uint64_t kHaloDesc = ((uint64_t)1 << 16) | ((uint64_t)((TC_HALO_W * 128) >> 4) << 32) |
+                                         ((uint64_t)1 << 46) | ((uint64_t)2 << 61);
+          for (int kc = 0; kc < kchunks; ++kc) {
+            mbar_wait(&afull_bar[hstage], hphase);
+            tc_fence_after();
+            const uint32_t ha = smem_u32(smem + hstage * TC_HALO_STAGE);
+            for (int tap = 0; tap < 9; ++tap) {
+              mbar_wait(&full_bar[stage], phase);
+              tc_fence_after();
+              const uint32_t toff = (uint32_t)((tap / 3) * TC_HALO_W + tap % 3) * 128u;
+              const uint64_t a_hi = kHaloDesc | (uint64_t)(((ha + toff) >> 4) & 0x3fffu);
+              const uint64_t a_lo = kHaloDesc | (uint64_t)(((ha + TC_HALO_PLANE + toff) >> 4) & 0x3fffu);
+              const uint32_t sb = smem_u32(ring + stage * STAGE_BYTES);
+              const uint64_t b_hi = umma_desc_kmajor_sw128(sb);
+              const uint64_t b_lo = umma_desc_kmajor_sw128(sb + B_BYTES);
+#pragma unroll
+              for (int k = 0; k < TC_BK / 16; ++k) {
+                const uint64_t ko = (uint64_t)(k * 2);
+                const uint32_t first = (kc > 0 || tap > 0 || k > 0) ? 1u : 0u;
+                if (kConcat) {
+                  constexpr uint32_t idesc2n = umma_idesc_bf16_f32(TC_BM, 2 * BN);
+                  umma_bf16(d_tmem, a_hi + ko, b_hi + ko, idesc2n, first);
+                  umma_bf16(d_tmem + 2 * BN, a_lo + ko, b_hi + ko, idesc, first);
+                } else if (PAIR) {
+                  umma_bf16_2sm(d_tmem, a_lo + ko, b_hi + ko, idesc, first);
+                  umma_bf16_2sm(d_tmem, a_hi + ko, b_lo + ko, idesc, 1u);
+                  umma_bf16_2sm(d_tmem, a_hi + ko, b_hi + ko, idesc, 1u);
+                } else {
+                  umma_bf16(d_tmem, a_lo + ko, b_hi + ko, idesc, first);
+                  umma_bf16(d_tmem, a_hi + ko, b_lo + ko, idesc, 1u);
+                  umma_bf16(d_tmem, a_hi + ko, b_hi + ko, idesc, 1u);
+                }
+              }
+              if (PAIR) umma_commit_2sm_mc(&empty_bar[stage], 0x3);
+              else umma_commit(&empty_bar[stage]);
+              if (++stage == STAGES) { stage = 0; phase ^= 1; }
+            }
+            if (PAIR) umma_commit_2sm_mc(&aempty_bar[hstage], 0x3);
+            else umma_commit(&aempty_bar[hstage]);
+            if (++hstage == NA) { hstage = 0; hphase ^= 1; }
+          }
+        } else {
         for (int kit = 0; kit < kiters; ++kit) {
           mbar_wait(&full_bar[stage], phase);
           tc_fence_after();
@@ -258,6 +385,7 @@ conv3x3_tc_kernel(const __grid_constant__ CUtensorMap tm_xhi, const __grid_const
           if (PAIR) umma_commit_2sm_mc(&empty_bar[stage], 0x3);
           else umma_commit(&empty_bar[stage]);
           if (++stage == STAGES) { stage = 0; phase ^= 1; }
+        }
         }
         // accumulator ready for the epilogue
         if (PAIR) umma_commit_2sm_mc(&tfull_bar[as], 0x3);
@@ -382,13 +510,15 @@ conv3x3_tc_kernel(const __grid_constant__ CUtensorMap tm_xhi, const __grid_const
 }
 
 // ---- host launcher --------------------------------------------------------------------------
-template <int BN, int STAGES, bool PAIR>
+template <int BN, int STAGES, bool PAIR, bool HALO = false, int NA = 0>
 static int launch_tc_variant(const CUtensorMap& xhi, const CUtensorMap& xlo, const CUtensorMap& whi,
                              const CUtensorMap& wlo, const ConvTcArgs& a, cudaStream_t s) {
-  constexpr int smem = STAGES * ConvTcSmem<BN, PAIR>::STAGE_BYTES + 1024 /*align slack*/ + 256 /*barriers*/;
+  constexpr int smem = ConvTcSmem<BN, PAIR, HALO, NA>::A_RING + STAGES * ConvTcSmem<BN, PAIR, HALO, NA>::STAGE_BYTES +
+                       1024 /*align slack*/ + 256 /*barriers*/;
+  static_assert(smem <= 232448, "shared-memory budget");
   static bool attr_done = false;
   if (!attr_done) {
-    IBL_CUDA_OK(cudaFuncSetAttribute(conv3x3_tc_kernel<BN, STAGES, PAIR>,
+    IBL_CUDA_OK(cudaFuncSetAttribute(conv3x3_tc_kernel<BN, STAGES, PAIR, HALO, NA>,
                                      cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
     attr_done = true;
   }
@@ -409,11 +539,11 @@ static int launch_tc_variant(const CUtensorMap& xhi, const CUtensorMap& xlo, con
     attr[0].val.clusterDim.z = 1;
     cfg.attrs = attr;
     cfg.numAttrs = 1;
-    IBL_CUDA_OK(cudaLaunchKernelEx(&cfg, conv3x3_tc_kernel<BN, STAGES, PAIR>, xhi, xlo, whi, wlo, a));
+    IBL_CUDA_OK(cudaLaunchKernelEx(&cfg, conv3x3_tc_kernel<BN, STAGES, PAIR, HALO, NA>, xhi, xlo, whi, wlo, a));
     return IBL_OK;
   }
   int grid = a.total_tiles < sms ? a.total_tiles : sms;
-  conv3x3_tc_kernel<BN, STAGES, PAIR><<<grid, 192, smem, s>>>(xhi, xlo, whi, wlo, a);
+  conv3x3_tc_kernel<BN, STAGES, PAIR, HALO, NA><<<grid, 192, smem, s>>>(xhi, xlo, whi, wlo, a);
   IBL_CUDA_OK(cudaGetLastError());
   return IBL_OK;
 }
@@ -436,6 +566,9 @@ int launch_conv3x3_tc(const __nv_bfloat16* x_hi, const __nv_bfloat16* x_lo, cons
     return (long long)cdiv(W, tw) * tw * cdiv(H, th) * th;
   };
   a.tw_log2 = (waste(16) <= waste(8)) ? 4 : 3;
+  // halo staging needs 16x8 patches (8-pixel row groups at a uniform stride); IBL_CONV_HALO=0 disables it
+  // (set below once the N tile is known: it pays on the 128-wide tiles only)
+  static const int halo_env = [] { const char* v = getenv("IBL_CONV_HALO"); return v ? atoi(v) : 1; }();
   const int TW = 1 << a.tw_log2, TH = 128 / TW;
   a.tiles_w = cdiv(W, TW);
   a.tiles_h = cdiv(H, TH);
@@ -450,12 +583,23 @@ int launch_conv3x3_tc(const __nv_bfloat16* x_hi, const __nv_bfloat16* x_lo, cons
     if (env_bn < 0) { const char* v = getenv("IBL_TC_BN"); env_bn = v ? atoi(v) : 0; }
     if (env_bn > 0 && !g_tc_bn_override && cout % env_bn == 0) bn = env_bn;
   }
+  // Halo staging: measured -12 % / -6 % on conv2_1 / conv2_2 (BN = 128, where the nine im2col boxes per chunk
+  // saturate the 64 B/clk L2->SM path), but +4..9 % on the 256-wide tiles (the tap views are not 1024-byte
+  // aligned, so the A operand costs extra shared-memory wavefronts that the N = 256 MMAs cannot hide) and
+  // neutral on conv1_2.  IBL_CONV_HALO=0: never, =2: every layer.
+  const bool halo = halo_env == 2 || (halo_env == 1 && bn == 128);
+  if (halo) {
+    a.tw_log2 = 3;
+    a.tiles_w = cdiv(W, 8);
+    a.tiles_h = cdiv(H, 16);
+  }
   // SM pairs for the 256-wide tiles (measured 3-7 % faster on conv4_x/conv5_x, neutral on conv3_x; the
   // 128-wide pair variant is 30 % SLOWER than one SM per tile and is only reachable with IBL_CONV_2SM=2).
   // IBL_CONV_2SM=0: one-SM kernels everywhere.
   static const int pair_env = [] { const char* v = getenv("IBL_CONV_2SM"); return v ? atoi(v) : 1; }();
   const long long patches = (long long)N * a.tiles_h * a.tiles_w;
-  const bool pair = pair_env && patches >= 2 && (bn == 256 || (bn == 128 && pair_env == 2));
+  const bool pair = pair_env && patches >= 2 && ((bn == 256 && cin >= 256) || pair_env == 2) && bn >= 128 &&
+                    !(halo && bn != 256);
   a.n_tiles = cout / bn;
   a.total_tiles = (int)((pair ? (patches + 1) / 2 : patches) * a.n_tiles);
   a.relu = relu; a.pool = pool;
@@ -468,7 +612,7 @@ int launch_conv3x3_tc(const __nv_bfloat16* x_hi, const __nv_bfloat16* x_lo, cons
   {
     uint64_t dims[4] = {(uint64_t)cin, (uint64_t)W, (uint64_t)H, (uint64_t)N};
     uint64_t str[3] = {(uint64_t)cin * 2, (uint64_t)W * cin * 2, (uint64_t)H * W * cin * 2};
-    uint32_t box[4] = {64, (uint32_t)TW, (uint32_t)TH, 1};
+    uint32_t box[4] = {64, (uint32_t)(halo ? TC_HALO_W : TW), (uint32_t)(halo ? TC_HALO_H : TH), 1};
     IBL_RET(make_tmap(&m_xhi, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 4, x_hi, dims, str, box));
     IBL_RET(make_tmap(&m_xlo, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 4, x_lo, dims, str, box));
   }
@@ -478,6 +622,12 @@ int launch_conv3x3_tc(const __nv_bfloat16* x_hi, const __nv_bfloat16* x_lo, cons
     uint32_t box[3] = {64, (uint32_t)(pair ? bn / 2 : bn), 1};
     IBL_RET(make_tmap(&m_whi, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 3, p.w_hi, dims, str, box));
     IBL_RET(make_tmap(&m_wlo, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 3, p.w_lo, dims, str, box));
+  }
+  if (halo) {
+    if (bn == 64) return launch_tc_variant<64, 4, false, true, 3>(m_xhi, m_xlo, m_whi, m_wlo, a, s);
+    if (bn == 128) return launch_tc_variant<128, 3, false, true, 2>(m_xhi, m_xlo, m_whi, m_wlo, a, s);
+    if (pair) return launch_tc_variant<256, 4, true, true, 2>(m_xhi, m_xlo, m_whi, m_wlo, a, s);
+    return launch_tc_variant<256, 2, false, true, 2>(m_xhi, m_xlo, m_whi, m_wlo, a, s);
   }
   if (bn == 64) return launch_tc_variant<64, 4, false>(m_xhi, m_xlo, m_whi, m_wlo, a, s);
   if (bn == 128) {
