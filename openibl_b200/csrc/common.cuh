@@ -85,6 +85,7 @@ int launch_conv1_1_tc(const float* x_nchw, const float* w_oihw, const float* bia
 // tc_netvlad.cu
 int debug_gemm_tn(const float* A, const float* B, float* C, cudaStream_t s);
 int netvlad_tc_units(int B, int S);
+int netvlad_tc_asum_parts(int G);   // partials of sum_s a per image the active kernel writes
 // tc_probe.cu
 int debug_umma_strided(const void* A, int rows, const void* B, int s0, int group_rows, int base_mode, float* D,
                        cudaStream_t s);

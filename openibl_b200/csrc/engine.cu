@@ -372,7 +372,7 @@ int ibl_netvlad_forward(ibl_engine* e, const float* feat, int nhwc, int N, int C
     IBL_RET(launch_row_sqnorm(feat, N * S_, C, e->ssq.as<float>(), s));
     const int G = netvlad_tc_units(N, S_);
     IBL_RET(e->nv_part.ensure((size_t)N * G * 64 * 512 * sizeof(float)));
-    IBL_RET(e->nv_asum.ensure((size_t)N * (G + 1) * 64 * sizeof(float)));
+    IBL_RET(e->nv_asum.ensure((size_t)N * (netvlad_tc_asum_parts(G) + 1) * 64 * sizeof(float)));
     IBL_RET(launch_netvlad_tc(xh, xh + ne, N, S_, wh, wh + nw, e->ssq.as<float>(), 1, centroids,
                               normalize_input != 0, e->nv_part.as<float>(), e->nv_asum.as<float>(), vlad_raw,
                               vlad_norm, s));
@@ -497,7 +497,7 @@ int ibl_extract(ibl_engine* e, const float* x, int N, int H, int W, unsigned fla
       }
       const int G = netvlad_tc_units(nb, Sp);
       IBL_RET(e->nv_part.ensure((size_t)nb * G * 64 * 512 * sizeof(float)));
-      IBL_RET(e->nv_asum.ensure((size_t)nb * (G + 1) * 64 * sizeof(float)));
+      IBL_RET(e->nv_asum.ensure((size_t)nb * (netvlad_tc_asum_parts(G) + 1) * 64 * sizeof(float)));
       const size_t nw = (size_t)64 * 512;
       IBL_RET(launch_netvlad_tc(fp.hi, fp.lo, nb, Sp, e->nvw_pl.as<__nv_bfloat16>(), e->nvw_pl.as<__nv_bfloat16>() + nw,
                                 e->ssq.as<float>(), fp.ssq_parts, e->nv_c, true, e->nv_part.as<float>(),

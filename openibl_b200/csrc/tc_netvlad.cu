@@ -454,14 +454,14 @@ netvlad_tc_kernel(const __grid_constant__ CUtensorMap tm_xhi, const __grid_const
 // grid (8, B): one warp per cluster row, 16 channels per lane held in registers.  Writes the raw VLAD
 // (if asked), the intra-normalised rows, and each row's squared norm for the global L2 pass.
 __global__ void __launch_bounds__(256)
-netvlad_finalize_rows_kernel(const float* __restrict__ part, const float* __restrict__ asum_part, int G,
+netvlad_finalize_rows_kernel(const float* __restrict__ part, const float* __restrict__ asum_part, int G, int AG,
                              const float* __restrict__ cent, float* __restrict__ vlad_raw /*nullable*/,
                              float* __restrict__ vlad_norm /*nullable*/, float* __restrict__ row_ss /*[B][64]*/) {
   const long long b = blockIdx.y;
   const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
   const int k = blockIdx.x * 8 + wid;
   float asum = 0.f;
-  for (int g = 0; g < G; ++g) asum += __ldg(asum_part + (b * G + g) * 64 + k);
+  for (int g = 0; g < AG; ++g) asum += __ldg(asum_part + (b * AG + g) * 64 + k);   // AG partials of sum_s a
   float v[16];
   float ss = 0.f;
 #pragma unroll
@@ -507,7 +507,22 @@ netvlad_finalize_l2_kernel(float* __restrict__ vlad_norm, const float* __restric
   }
 }
 
+// tc_netvlad4.cu: the 4-CTA-cluster kernel.  Opt-in (IBL_NV_CLUSTER=1): it is correct (same parity tests) and
+// reads every feature byte once, but measures 62-77 us against 44 us for the one-SM kernel above at B=32 --
+// the two DSMEM exchanges per tile (48 KiB out per CTA at ~20 B/clk) plus their round trips sit on the
+// critical path and two x buffers are not enough to hide them (profiles/README.md).
+int netvlad_c4_units(int B, int S);
+int launch_netvlad_c4(const CUtensorMap& mx_hi, const CUtensorMap& mx_lo, const CUtensorMap& mw_hi,
+                      const CUtensorMap& mw_lo, int B, int S, int G, const float* ssq, int ssq_parts,
+                      bool normalize_input, float* part, float* asum_part, cudaStream_t s);
+static bool nv_cluster() {
+  static const bool on = [] { const char* v = getenv("IBL_NV_CLUSTER"); return v && atoi(v) != 0; }();
+  return on;
+}
+int netvlad_tc_asum_parts(int G) { return nv_cluster() ? 4 * G : G; }
+
 int netvlad_tc_units(int B, int S) {
+  if (nv_cluster()) return netvlad_c4_units(B, S);
   int sms = 148;
   int dev = 0;
   cudaGetDevice(&dev);
@@ -559,9 +574,15 @@ int launch_netvlad_tc(const __nv_bfloat16* x_hi, const __nv_bfloat16* x_lo, int 
   cudaGetDevice(&dev);
   cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
   const int units = B * a.G;
-  netvlad_tc_kernel<<<units < sms ? units : sms, 192, smem, s>>>(mx_hi, mx_lo, mw_hi, mw_lo, a);
-  IBL_CUDA_OK(cudaGetLastError());
-  if (dbg_on) {   // print phase stamps of a few CTAs (ns relative to the earliest stamp)
+  const int AG = netvlad_tc_asum_parts(a.G);
+  if (nv_cluster()) {
+    IBL_RET(launch_netvlad_c4(mx_hi, mx_lo, mw_hi, mw_lo, B, S, a.G, ssq, ssq_parts, normalize_input, part,
+                              asum_part, s));
+  } else {
+    netvlad_tc_kernel<<<units < sms ? units : sms, 192, smem, s>>>(mx_hi, mx_lo, mw_hi, mw_lo, a);
+    IBL_CUDA_OK(cudaGetLastError());
+  }
+  if (dbg_on && !nv_cluster()) {   // print phase stamps of a few CTAs (ns relative to the earliest stamp)
     cudaStreamSynchronize(s);
     static unsigned long long h[148 * 32];
     cudaMemcpy(h, dbg_dev, sizeof(h), cudaMemcpyDeviceToHost);
@@ -573,8 +594,8 @@ int launch_netvlad_tc(const __nv_bfloat16* x_hi, const __nv_bfloat16* x_lo, int 
       fprintf(stderr, "\n");
     }
   }
-  float* row_ss = asum_part + (size_t)units * 64;   // caller sizes asum_part as [units + B][64]
-  netvlad_finalize_rows_kernel<<<dim3(8, B), 256, 0, s>>>(part, asum_part, a.G, cent, vlad_raw, vlad_norm, row_ss);
+  float* row_ss = asum_part + (size_t)B * AG * 64;   // caller sizes asum_part as [B * (AG + 1)][64]
+  netvlad_finalize_rows_kernel<<<dim3(8, B), 256, 0, s>>>(part, asum_part, a.G, AG, cent, vlad_raw, vlad_norm, row_ss);
   IBL_CUDA_OK(cudaGetLastError());
   if (vlad_norm) {
     netvlad_finalize_l2_kernel<<<dim3(8, B), 256, 0, s>>>(vlad_norm, row_ss);
