@@ -539,7 +539,8 @@ int ibl_extract_host(ibl_engine* e, const float* x_host, int N, int H, int W, un
   }
   const size_t img_elems = (size_t)3 * H * W;
   // uneven split: only the first (small) part's copy is exposed; the rest streams in behind its compute
-  const int n_first = halves == 2 ? (N / 4 > 0 ? N / 4 : 1) : N;
+  static const int split_div = [] { const char* v = getenv("IBL_HOST_SPLIT"); const int d = v ? atoi(v) : 0; return d >= 2 ? d : 4; }();
+  const int n_first = halves == 2 ? (N / split_div > 0 ? N / split_div : 1) : N;
   for (int i = 0; i < halves; ++i) {
     const int n0 = i == 0 ? 0 : n_first, nb = i == 0 ? n_first : N - n_first;
     IBL_CUDA_OK(cudaMemcpyAsync(e->stage_in.as<float>() + n0 * img_elems, x_host + n0 * img_elems,
