@@ -276,6 +276,25 @@ def main():
         dist.all_reduce(e2e_ms, op=dist.ReduceOp.MAX)
     e2e_val = world * BATCH * args.steps / (float(e2e_ms.item()) / 1000.0)
 
+    # ---- the same from decoded uint8 HWC images (ToTensor + Normalize on the device) -------------
+    from openibl_b200.utils.data import _MEAN, _STD
+    gu = torch.Generator().manual_seed(11 + rank)
+    xs_u8 = [torch.randint(0, 256, (BATCH, H, W, 3), dtype=torch.uint8, generator=gu).pin_memory() for _ in range(2)]
+    for i in range(2):
+        eng.extract_host_u8(xs_u8[i % 2], out_host, _MEAN, _STD, pca=True)
+    barrier()
+    u0, u1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    u0.record()
+    for i in range(args.steps):
+        eng.extract_host_u8(xs_u8[i % 2], out_host, _MEAN, _STD, pca=True)
+    u1.record()
+    torch.cuda.synchronize()
+    u8_ms = torch.tensor([u0.elapsed_time(u1)], device=dev)
+    if world > 1:
+        dist.all_reduce(u8_ms, op=dist.ReduceOp.MAX)
+    e2e_u8_val = world * BATCH * args.steps / (float(u8_ms.item()) / 1000.0)
+    del xs_u8
+
     # ---- retrieval: 6.8k x (10k per rank) sharded distance + top-k + all-gather merge ----------
     from openibl_b200.evaluators import sharded_topk
     q, db, gt = synth.make_gallery(NDB, NQ, DIM, seed_db=2 + rank)
@@ -309,6 +328,10 @@ def main():
             "gpu_launches": int(launches), "clocks": clocks, "roofline": roofline,
             "e2e": {"value": e2e_val, "unit": "images/s",
                     "h2d_bytes_per_step": BATCH * 3 * H * W * 4, "d2h_bytes_per_step": BATCH * 4096 * 4},
+            "e2e_u8": {"value": e2e_u8_val, "unit": "images/s", "h2d_bytes_per_step": BATCH * 3 * H * W,
+                       "d2h_bytes_per_step": BATCH * 4096 * 4,
+                       "note": "same path fed with decoded uint8 HWC images; ToTensor+Normalize "
+                               "(ibl/utils/data/__init__.py:37-42) runs on the device"},
             "retrieval": {"metric": "query_db_pairs_per_sec", "value": pairs, "unit": "pairs/s",
                           "workload": f"{NQ} q x {NDB} db/GPU x {DIM}-d, top-{TOPK}, sharded + all-gather merge",
                           "ms": float(r_ms.item()),

@@ -132,6 +132,19 @@ int ibl_extract(ibl_engine* e, const float* x_nchw, int N, int H, int W, unsigne
 int ibl_extract_host(ibl_engine* e, const float* x_nchw_host, int N, int H, int W,
                      unsigned flags, float* out_host, float* pool_host, void* stream);
 
+/* ---- input side: ToTensor + Normalize on the GPU ----------------------------- */
+/* The reference's test transform after the resize (ibl/utils/data/__init__.py:37-42: T.ToTensor(),
+ * T.Normalize(mean, std)) applied to decoded uint8 HWC pixels: out[n,c,h,w] = ((x[n,h,w,c]/255) - mean[c]) / std[c],
+ * IEEE fp32 operations in that order (bit-identical to torchvision on the CPU).  x_nhwc device uint8 [N,H,W,3],
+ * mean3/std3 HOST float[3], out device fp32 [N,3,H,W]. */
+int ibl_preprocess_u8(ibl_engine* e, const uint8_t* x_nhwc, int N, int H, int W, const float* mean3,
+                      const float* std3, float* out_nchw, void* stream);
+/* ibl_extract_host for a loader that hands over decoded uint8 HWC images (Preprocessor.__getitem__,
+ * ibl/utils/data/preprocessor.py:31-42, minus the CPU transform): H2D of N*H*W*3 bytes (a quarter of the fp32
+ * tensor), the transform above on the device, the extraction path, D2H of the descriptors, stream sync. */
+int ibl_extract_host_u8(ibl_engine* e, const uint8_t* x_nhwc_host, int N, int H, int W, const float* mean3,
+                        const float* std3, unsigned flags, float* out_host, float* pool_host, void* stream);
+
 /* ---- stage (iii-b): distance + ranking ------------------------------------- */
 /* pairwise_distance(features) with query = gallery = None (evaluators.py:106-114):
  * out[i,j] = 2|x_i|^2 - 2 x_i.x_j, x [n,d], out [n,n]. */

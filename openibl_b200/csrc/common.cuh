@@ -63,6 +63,8 @@ int launch_conv1_1(const float* x_nchw, const ConvParams& p, int N, int H, int W
                    float* y_nhwc, __nv_bfloat16* y_hi, __nv_bfloat16* y_lo, cudaStream_t s);
 int launch_maxpool2x2(const float* x, int N, int H, int W, int C, float* y, cudaStream_t s);
 int launch_nhwc_to_nchw(const float* x, int N, int S, int C, float* y, cudaStream_t s);
+int launch_u8_hwc_to_nchw_norm(const uint8_t* x, int N, int H, int W, const float* mean, const float* stdv, float* y,
+                               cudaStream_t s);
 int launch_global_maxpool_nhwc(const float* x, int N, int S, int C, float* y, cudaStream_t s);
 int launch_planes_to_f32(const __nv_bfloat16* hi, const __nv_bfloat16* lo, size_t n, float* y,
                          cudaStream_t s);

@@ -75,7 +75,7 @@ struct ibl_engine {
   DevBuf nv_assign, nv_inv, nv_raw, vlad;
   DevBuf pca_partial;
   DevBuf qn, dbn, dist_chunk, cand_d, cand_i;
-  DevBuf stage_in, stage_out, stage_out2;
+  DevBuf stage_in, stage_out, stage_out2, stage_u8;
   DevBuf q_pl, db_pl, v_pl, pca_pl;     // bf16 hi|lo planes of queries, database shard, descriptors, PCA W
   const float* pca_pl_src = nullptr;    // W pointer the cached planes were made from
   DevBuf mrg_d, mrg_i;
@@ -235,7 +235,7 @@ int ibl_engine_destroy(ibl_engine* e) {
   if (e->copy_stream) { cudaStreamDestroy(e->copy_stream); cudaEventDestroy(e->copy_ev[0]); cudaEventDestroy(e->copy_ev[1]); }
   DevBuf* bufs[] = {&e->act[0], &e->act[1], &e->feat, &e->nv_assign, &e->nv_inv, &e->nv_raw, &e->vlad,
                     &e->pca_partial, &e->qn, &e->dbn, &e->dist_chunk, &e->cand_d, &e->cand_i,
-                    &e->stage_in, &e->stage_out, &e->stage_out2, &e->q_pl, &e->db_pl, &e->v_pl, &e->pca_pl,
+                    &e->stage_in, &e->stage_out, &e->stage_out2, &e->stage_u8, &e->q_pl, &e->db_pl, &e->v_pl, &e->pca_pl,
                     &e->mrg_d, &e->mrg_i, &e->ssq, &e->nv_part, &e->nv_asum, &e->nvw_pl};
   for (DevBuf* b : bufs) b->release();
   delete e;
@@ -559,6 +559,62 @@ int ibl_extract_host(ibl_engine* e, const float* x_host, int N, int H, int W, un
   if ((flags & IBL_OUT_POOL) && pool_host)
     IBL_CUDA_OK(cudaMemcpyAsync(pool_host, e->stage_out2.p, (size_t)N * 512 * sizeof(float),
                                 cudaMemcpyDeviceToHost, S(stream)));
+  IBL_CUDA_OK(cudaStreamSynchronize(S(stream)));
+  return IBL_OK;
+}
+
+int ibl_preprocess_u8(ibl_engine* e, const uint8_t* x_nhwc, int N, int H, int W, const float* mean3,
+                      const float* std3, float* out_nchw, void* stream) {
+  IBL_REQUIRE(e && x_nhwc && mean3 && std3 && out_nchw, "null argument");
+  IBL_REQUIRE(N >= 1 && H >= 1 && W >= 1, "empty image batch");
+  IBL_REQUIRE(std3[0] != 0.f && std3[1] != 0.f && std3[2] != 0.f, "zero std");
+  DeviceGuard g(e->device);
+  e->launches++;
+  return launch_u8_hwc_to_nchw_norm(x_nhwc, N, H, W, mean3, std3, out_nchw, S(stream));
+}
+
+int ibl_extract_host_u8(ibl_engine* e, const uint8_t* x_nhwc_host, int N, int H, int W, const float* mean3,
+                        const float* std3, unsigned flags, float* out_host, float* pool_host, void* stream) {
+  IBL_REQUIRE(e && x_nhwc_host && mean3 && std3 && out_host, "null argument");
+  IBL_REQUIRE(N >= 1 && H >= 16 && W >= 16, "VGG16 trunk needs N>=1 and H,W>=16");
+  IBL_REQUIRE(std3[0] != 0.f && std3[1] != 0.f && std3[2] != 0.f, "zero std");
+  DeviceGuard g(e->device);
+  const bool pca = (flags & IBL_OUT_PCA) != 0;
+  const int out_dim = pca ? e->pca_P : e->nv_K * e->nv_C;
+  const size_t img_px = (size_t)H * W;
+  IBL_RET(e->stage_u8.ensure((size_t)N * img_px * 3));
+  IBL_RET(e->stage_in.ensure((size_t)N * img_px * 3 * sizeof(float)));
+  IBL_RET(e->stage_out.ensure((size_t)N * out_dim * sizeof(float)));
+  if (flags & IBL_OUT_POOL) IBL_RET(e->stage_out2.ensure((size_t)N * 512 * sizeof(float)));
+  if (!e->copy_stream) {
+    IBL_CUDA_OK(cudaStreamCreateWithFlags(&e->copy_stream, cudaStreamNonBlocking));
+    IBL_CUDA_OK(cudaEventCreateWithFlags(&e->copy_ev[0], cudaEventDisableTiming));
+    IBL_CUDA_OK(cudaEventCreateWithFlags(&e->copy_ev[1], cudaEventDisableTiming));
+  }
+  // same two-part overlap as ibl_extract_host, with a quarter of the bytes on the wire
+  const int parts = N >= 16 ? 2 : 1;
+  const int n_first = parts == 2 ? N / 4 : N;
+  uint8_t* du8 = e->stage_u8.as<uint8_t>();
+  for (int i = 0; i < parts; ++i) {
+    const int n0 = i == 0 ? 0 : n_first, nb = i == 0 ? n_first : N - n_first;
+    IBL_CUDA_OK(cudaMemcpyAsync(du8 + n0 * img_px * 3, x_nhwc_host + n0 * img_px * 3, nb * img_px * 3,
+                                cudaMemcpyHostToDevice, e->copy_stream));
+    IBL_CUDA_OK(cudaEventRecord(e->copy_ev[i], e->copy_stream));
+  }
+  for (int i = 0; i < parts; ++i) {
+    const int n0 = i == 0 ? 0 : n_first, nb = i == 0 ? n_first : N - n_first;
+    IBL_CUDA_OK(cudaStreamWaitEvent(S(stream), e->copy_ev[i], 0));
+    float* xin = e->stage_in.as<float>() + n0 * img_px * 3;
+    IBL_RET(launch_u8_hwc_to_nchw_norm(du8 + n0 * img_px * 3, nb, H, W, mean3, std3, xin, S(stream)));
+    e->launches++;
+    IBL_RET(ibl_extract(e, xin, nb, H, W, flags, e->stage_out.as<float>() + (size_t)n0 * out_dim,
+                        (flags & IBL_OUT_POOL) ? e->stage_out2.as<float>() + (size_t)n0 * 512 : nullptr, stream));
+  }
+  IBL_CUDA_OK(cudaMemcpyAsync(out_host, e->stage_out.p, (size_t)N * out_dim * sizeof(float), cudaMemcpyDeviceToHost,
+                              S(stream)));
+  if ((flags & IBL_OUT_POOL) && pool_host)
+    IBL_CUDA_OK(cudaMemcpyAsync(pool_host, e->stage_out2.p, (size_t)N * 512 * sizeof(float), cudaMemcpyDeviceToHost,
+                                S(stream)));
   IBL_CUDA_OK(cudaStreamSynchronize(S(stream)));
   return IBL_OK;
 }

@@ -295,6 +295,36 @@ int launch_nhwc_to_nchw(const float* x, int N, int S, int C, float* y, cudaStrea
   return IBL_OK;
 }
 
+// ToTensor + Normalize of the reference's test transform (ibl/utils/data/__init__.py:37-42, torchvision
+// semantics): y[n,c,h,w] = ((x[n,h,w,c] / 255) - mean[c]) / std[c] with IEEE fp32 division and no contraction,
+// so the result is bit-identical to the CPU transform.  uint8 HWC (decoder layout) -> fp32 NCHW.
+// One thread per pixel: 3 byte loads (the warp covers 96 contiguous bytes), 3 coalesced plane stores.
+__global__ void u8_hwc_to_nchw_norm_kernel(const uint8_t* __restrict__ x, float* __restrict__ y, long long hw,
+                                           long long total, float m0, float m1, float m2, float s0, float s1,
+                                           float s2) {
+  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total;
+       i += (long long)gridDim.x * blockDim.x) {
+    const long long n = i / hw, p = i - n * hw;
+    const uint8_t* px = x + i * 3;
+    float* o = y + n * 3 * hw + p;
+    o[0] = __fdiv_rn(__fsub_rn(__fdiv_rn((float)px[0], 255.f), m0), s0);
+    o[hw] = __fdiv_rn(__fsub_rn(__fdiv_rn((float)px[1], 255.f), m1), s1);
+    o[2 * hw] = __fdiv_rn(__fsub_rn(__fdiv_rn((float)px[2], 255.f), m2), s2);
+  }
+}
+
+int launch_u8_hwc_to_nchw_norm(const uint8_t* x, int N, int H, int W, const float* mean, const float* stdv, float* y,
+                               cudaStream_t s) {
+  const long long hw = (long long)H * W, total = hw * N;
+  unsigned blocks = (unsigned)((total + 255) / 256);
+  if (blocks > 148 * 16) blocks = 148 * 16;
+  if (!blocks) blocks = 1;
+  u8_hwc_to_nchw_norm_kernel<<<blocks, 256, 0, s>>>(x, y, hw, total, mean[0], mean[1], mean[2], stdv[0], stdv[1],
+                                                    stdv[2]);
+  IBL_CUDA_OK(cudaGetLastError());
+  return IBL_OK;
+}
+
 // AdaptiveMaxPool2d(1) over an NHWC map (vgg.py:67-68): [N,S,C] -> [N,C]
 __global__ void global_maxpool_kernel(const float* __restrict__ x, float* __restrict__ y, int S,
                                       int C) {

@@ -231,6 +231,38 @@ class Engine:
                                         _stream(self.device)), "ibl_extract_host")
         return out_host
 
+    # ---- input side: ToTensor + Normalize on the device (utils/data/__init__.py:37-42) ------
+    @staticmethod
+    def _norm_consts(mean, std):
+        import ctypes
+        m = (ctypes.c_float * 3)(*[float(v) for v in mean])
+        s = (ctypes.c_float * 3)(*[float(v) for v in std])
+        return m, s
+
+    def preprocess_u8(self, x_u8_nhwc: torch.Tensor, mean, std) -> torch.Tensor:
+        """uint8 [N,H,W,3] on the GPU -> fp32 [N,3,H,W] = ((x/255) - mean) / std, bit-identical to torchvision."""
+        x = _require_cuda(x_u8_nhwc, "images", dtype=torch.uint8)
+        N, H, W, C = x.shape
+        assert C == 3
+        out = torch.empty(N, 3, H, W, device=x.device)
+        m, s = self._norm_consts(mean, std)
+        check(self.lib.ibl_preprocess_u8(self.h, _ptr(x), N, H, W, m, s, _ptr(out), _stream(self.device)),
+              "ibl_preprocess_u8")
+        return out
+
+    def extract_host_u8(self, x_u8_host: torch.Tensor, out_host: torch.Tensor, mean, std, pca=False,
+                        pool_host: Optional[torch.Tensor] = None) -> torch.Tensor:
+        """HOST uint8 [N,H,W,3] in / HOST descriptors out: a quarter of extract_host's H2D bytes."""
+        assert not x_u8_host.is_cuda and not out_host.is_cuda and x_u8_host.is_contiguous() and out_host.is_contiguous()
+        assert x_u8_host.dtype == torch.uint8 and out_host.dtype == torch.float32
+        N, H, W, C = x_u8_host.shape
+        assert C == 3
+        flags = OUT_VLAD | (OUT_PCA if pca else 0) | (OUT_POOL if pool_host is not None else 0)
+        m, s = self._norm_consts(mean, std)
+        check(self.lib.ibl_extract_host_u8(self.h, _ptr(x_u8_host), N, H, W, m, s, flags, _ptr(out_host),
+                                           _ptr(pool_host), _stream(self.device)), "ibl_extract_host_u8")
+        return out_host
+
     # ---- retrieval -----------------------------------------------------------------------
     def l2dist_dense(self, q: torch.Tensor, db: torch.Tensor) -> torch.Tensor:
         q = _require_cuda(q, "queries")

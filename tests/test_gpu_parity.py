@@ -205,6 +205,27 @@ def test_shapes_tokyo_like_and_microbatching(eng, O):
     assert torch.equal(out_host2, got.cpu())
 
 
+def test_u8_preprocess_bit_exact_and_host_u8_path(eng):
+    """SURVEY 8(f) rank 4 (input side): ToTensor + Normalize of get_transformer_test
+    (ibl/utils/data/__init__.py:37-42) on the device, bit-identical to the CPU transform, and the uint8 host
+    entry point giving exactly the descriptors of the fp32 host entry point."""
+    from openibl_b200.utils.data import _MEAN, _STD
+    sd = synth.make_state_dict(seed=0, sharp=True, with_pca=True, pca_dim=128)
+    _bind(eng, sd)
+    gen = torch.Generator().manual_seed(77)
+    u8 = torch.randint(0, 256, (18, 48, 64, 3), dtype=torch.uint8, generator=gen)
+    # torchvision semantics: ToTensor = HWC uint8 -> CHW float / 255; Normalize = (t - mean) / std
+    ref = u8.permute(0, 3, 1, 2).float().div(255)
+    ref = (ref - torch.tensor(_MEAN).view(1, 3, 1, 1)) / torch.tensor(_STD).view(1, 3, 1, 1)
+    got = eng.preprocess_u8(u8.cuda(), _MEAN, _STD).cpu()
+    assert torch.equal(got, ref.contiguous())
+    out_f = torch.empty(18, 128).pin_memory()
+    out_u = torch.empty(18, 128).pin_memory()
+    eng.extract_host(ref.contiguous().pin_memory(), out_f, pca=True)
+    eng.extract_host_u8(u8.pin_memory(), out_u, _MEAN, _STD, pca=True)
+    assert torch.equal(out_f, out_u)
+
+
 def test_models_api_drop_in(eng):
     """The nn.Module mirror (what examples/test.py builds, :58-70) gives the golden outputs."""
     from ibl import models
@@ -357,6 +378,30 @@ def test_pca_unit_vs_reference(eng):
         eng.set_pca(w, b)                       # registers (and, for tcgen05, re-lays-out) W
         out = eng.pca_l2(v.cuda(), w, b)
         assert rel_l2(out.cpu(), g["out"]) < tol, name
+
+
+def test_pca_fit_load_infer_roundtrip_vs_oracle(eng, O, tmp_path):
+    """PCA.train on the GPU (pca.py:28-84), PCA.load (pca.py:86-106), PCA.infer
+    (pca.py:108-123) end to end.  Eigenvector signs are arbitrary, so the whitened outputs are compared
+    through sign-invariant quantities: |y| per component and all pairwise distances."""
+    from openibl_b200.pca import PCA
+    gen = torch.Generator().manual_seed(31)
+    n_pts, n_dims, P = 700, 512, 64
+    basis = torch.randn(n_dims, n_dims, generator=gen)
+    x = (torch.randn(n_pts, n_dims, generator=gen) * torch.logspace(0, -2, n_dims)) @ basis
+    x = torch.nn.functional.normalize(x + 0.1 * torch.randn(n_dims, generator=gen), dim=1)
+    pca = PCA(pca_n_components=P, pca_whitening=True, pca_parameters_path=str(tmp_path / "pca.h5"))
+    pca.train(x.cuda())
+    pca.load(gpu=0)
+    assert tuple(pca.weight.shape) == (P, n_dims, 1, 1) and tuple(pca.bias.shape) == (P,)
+    q = x[:50].cuda()
+    got = pca.infer(q).cpu()
+    U, lams, mu, _ = O.pca_train(x.clone(), n_components=P)
+    w, b = O.pca_load(U, lams, mu, n_components=P)
+    want = O.pca_whiten(x[:50], w, b)
+    assert rel_l2(got.abs(), want.abs()) < 2e-3, rel_l2(got.abs(), want.abs())
+    dg, dw = torch.cdist(got.double(), got.double()), torch.cdist(want.double(), want.double())
+    assert float((dg - dw).abs().max()) < 2e-3
 
 
 def test_pca_full_size_vs_oracle(eng, O):

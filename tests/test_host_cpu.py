@@ -166,3 +166,31 @@ def test_sharded_topk_world2_gloo():
         [p.join(180) for p in procs]
         assert all(p.exitcode == 0 for p in procs)
         assert ret.get(0) is True and ret.get(1) is True
+
+
+def _pca_fixture(n_pts, n_dims, seed):
+    g = torch.Generator().manual_seed(seed)
+    basis = torch.randn(n_dims, n_dims, generator=g)
+    scale = torch.logspace(0, -2, n_dims)
+    return (torch.randn(n_pts, n_dims, generator=g) * scale) @ basis + torch.randn(n_dims, generator=g)
+
+
+def test_pca_train_storage_roundtrip_matches_oracle(tmp_path):
+    """PCA.train (reference pca.py:28-84) on CPU: both the covariance branch (n_dims <= n_pts) and the dual
+    branch (n_dims > n_pts), parameters written and read back through the h5-free store; eigenvectors are
+    compared up to sign, eigenvalues exactly, against the oracle's restatement."""
+    from openibl_b200.pca import PCA
+    for n_pts, n_dims, P in ((300, 64, 16), (40, 96, 12)):
+        x = _pca_fixture(n_pts, n_dims, seed=n_pts)
+        path = str(tmp_path / f"pca_{n_pts}.h5")
+        pca = PCA(pca_n_components=P, pca_whitening=True, pca_parameters_path=path)
+        pca.train(x.clone())
+        got = pca._read()
+        U, lams, mu, Utmu = O.pca_train(x.clone(), n_components=P)
+        k = min(P, got["U"].shape[1])
+        np.testing.assert_allclose(got["lams"][:k], lams[:k], rtol=2e-4)
+        np.testing.assert_allclose(got["mu"].reshape(-1), mu.reshape(-1), rtol=1e-5, atol=1e-6)
+        # well-separated spectrum: |cos| between matching eigenvectors is 1
+        cos = np.abs((got["U"][:, :k] * U[:, :k]).sum(0))
+        assert cos.min() > 1 - 1e-3, cos.min()
+        assert os.path.isfile(path)      # examples/test.py:111 checks osp.isfile(pca_parameters_path)
