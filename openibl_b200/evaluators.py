@@ -201,9 +201,6 @@ class Evaluator(object):
         else:
             features = extract_features(self.model, query_loader, dataset, vlad=vlad, pca=pca, gpu=gpu,
                                         sync_gather=sync_gather)
-        if rerank:
-            raise NotImplementedError("k-reciprocal re-ranking (ibl/utils/rerank.py) is outside the "
-                                      "accelerated path (SURVEY 8f rank 3)")
         rank, world = _rank_world()
         dev = torch.device("cuda", torch.cuda.current_device() if gpu is None else gpu)
         x = torch.stack([features[f] for f, _, _, _ in query]).to(dev)
@@ -220,4 +217,17 @@ class Evaluator(object):
             print("Recall Scores:")
             for i, kk in enumerate((1, 5, 10)):
                 print("  top-{:<4}{:12.1%}".format(kk, recalls[i]))
-        return recalls
+        if not rerank:
+            return recalls
+        # evaluators.py:194-201: k-reciprocal re-ranking needs the dense q-g, q-q and g-g matrices; they are
+        # built on the GPU (tcgen05 dense distance tiles) and re-ranked there (utils/rerank.py), rank 0 only,
+        # as in the reference (the other ranks score the original matrix).
+        eng = Engine.get(dev)
+        y = torch.stack([features[f] for f, _, _, _ in gallery]).to(dev)
+        distmat = eng.l2dist_dense(x, y)
+        if self.rank == 0:
+            print("Applying re-ranking ...")
+            from .utils.rerank import re_ranking
+            distmat = re_ranking(distmat, eng.l2dist_dense(x, x), eng.l2dist_dense(y, y), k1=rr_topk, k2=1,
+                                 lambda_value=lambda_value)
+        return evaluate_all(distmat, ground_truth, gallery, nms=nms)

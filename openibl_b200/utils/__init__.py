@@ -18,4 +18,4 @@ def to_torch(ndarray):
     return ndarray
 
 
-from . import dist_utils, logging, meters, serialization, data  # noqa: E402,F401
+from . import dist_utils, logging, meters, serialization, data, rerank  # noqa: E402,F401

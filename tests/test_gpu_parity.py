@@ -455,6 +455,29 @@ def test_retrieval_vs_reference_golden(eng):
     assert np.abs(sd_.numpy() - g["self_dist"]).max() < 2e-5
 
 
+def test_rerank_on_gpu_distances_vs_reference_golden(eng):
+    """Evaluator.evaluate(rerank=True) path (evaluators.py:194-199): dense q-g / q-q / g-g distances from the
+    tcgen05 dense kernel, k-reciprocal re-ranking on the device; against the unmodified reference function run on
+    the reference's own fp32 distances (tests/golden/rerank.npz)."""
+    from openibl_b200.utils.rerank import re_ranking
+    g = load_golden("rerank")
+    for name in "abc":
+        k1, k2, lam = g[f"{name}_params"]
+        q, db = torch.from_numpy(g[f"{name}_q"]).cuda(), torch.from_numpy(g[f"{name}_db"]).cuda()
+        pad = (-q.shape[1]) % 64                     # the tensor-core distance path wants dim % 64 == 0
+        if pad:
+            q, db = torch.nn.functional.pad(q, (0, pad)), torch.nn.functional.pad(db, (0, pad))
+        qg, qq, gg = eng.l2dist_dense(q, db), eng.l2dist_dense(q, q), eng.l2dist_dense(db, db)
+        # |x|^2 + |y|^2 - 2xy on values of 2-3: a few fp32 ulps between two evaluation orders
+        assert float((qg.cpu() - torch.from_numpy(g[f"{name}_qg"])).abs().max()) < 3e-5
+        out = re_ranking(qg, qq, gg, k1=int(k1), k2=int(k2), lambda_value=float(lam))
+        assert out.is_cuda
+        ref = torch.from_numpy(g[f"{name}_final"])
+        # a near-tie in a neighbour list may flip under 1e-6 distance noise and move a few entries; the bulk agrees
+        close = ((out.cpu() - ref).abs() < 1e-4).float().mean()
+        assert close > 0.995, (name, float(close))
+
+
 def test_topk_edge_cases(eng, O):
     q, db, _ = synth.make_gallery(n_db=700, n_q=9, dim=64, sigma=0.5)
     qd, dbd = q.cuda(), db.cuda()

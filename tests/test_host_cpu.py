@@ -194,3 +194,19 @@ def test_pca_train_storage_roundtrip_matches_oracle(tmp_path):
         cos = np.abs((got["U"][:, :k] * U[:, :k]).sum(0))
         assert cos.min() > 1 - 1e-3, cos.min()
         assert os.path.isfile(path)      # examples/test.py:111 checks osp.isfile(pca_parameters_path)
+
+
+def test_rerank_matches_reference_golden():
+    """k-reciprocal re-ranking (ibl/utils/rerank.py:32-100, called from evaluators.py:194-199) restated as dense
+    set algebra: same distances as the unmodified reference function on three seeded cases (k2 = 1 as the
+    evaluator calls it, and k2 = 3 with query expansion)."""
+    from ibl.utils.rerank import re_ranking
+    g = load_golden("rerank")
+    for name in "abc":
+        k1, k2, lam = g[f"{name}_params"]
+        out = re_ranking(g[f"{name}_qg"], g[f"{name}_qq"], g[f"{name}_gg"], k1=int(k1), k2=int(k2), lambda_value=float(lam))
+        assert isinstance(out, np.ndarray) and out.shape == g[f"{name}_final"].shape
+        np.testing.assert_allclose(out, g[f"{name}_final"], atol=2e-6, rtol=0)
+        t = re_ranking(torch.from_numpy(g[f"{name}_qg"]), torch.from_numpy(g[f"{name}_qq"]), torch.from_numpy(g[f"{name}_gg"]),
+                       k1=int(k1), k2=int(k2), lambda_value=float(lam))
+        assert torch.is_tensor(t) and np.allclose(t.numpy(), out)
