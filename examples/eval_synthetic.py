@@ -62,6 +62,9 @@ def main():
     ap.add_argument("--test-batch-size", type=int, default=8)
     ap.add_argument("--seed", type=int, default=0)
     ap.add_argument("--expect-recalls", default="", help="comma-separated recalls to assert (tests)")
+    ap.add_argument("--rerank", action="store_true", help="k-reciprocal re-ranking, as examples/test.py --rerank")
+    ap.add_argument("--rr-topk", type=int, default=25)
+    ap.add_argument("--lambda-value", type=float, default=0.0)
     args = ap.parse_args()
 
     init_dist(args.launcher, args)                        # one process per GPU, NCCL
@@ -88,7 +91,8 @@ def main():
     evaluator = Evaluator(model)
     dataset = sorted(list(set(ds.q_test) | set(ds.db_test)))
     recalls = evaluator.evaluate(loader(ds.q_test), dataset, ds.q_test, ds.db_test, ds.test_pos,
-                                 gallery_loader=loader(ds.db_test), vlad=True, pca=None, gpu=args.gpu)
+                                 gallery_loader=loader(ds.db_test), vlad=True, pca=None, gpu=args.gpu,
+                                 rerank=args.rerank, rr_topk=args.rr_topk, lambda_value=args.lambda_value)
     synchronize()
     if args.rank == 0:
         print("RECALLS " + ",".join("%.6f" % r for r in recalls))
