@@ -70,6 +70,9 @@ CONV_CASES = [
     (1, 35, 45, 64, 64, True, True),         # odd sizes: floor pooling, partial patches
     (2, 17, 23, 256, 512, False, False),     # no ReLU (conv5_3-like), two N tiles
     (1, 60, 80, 512, 512, True, True),
+    (1, 16, 24, 256, 256, True, False),      # 3 patches: the SM-pair kernel's last pair has an idle peer
+    (3, 30, 40, 512, 512, False, False),     # conv5-like, 30 patches, pair tiles + per-pixel sum of squares path
+    (1, 33, 17, 128, 128, True, True),       # halo staging with ragged borders on both axes + fused pool
 ]
 
 
