@@ -40,7 +40,6 @@ struct Nv4Args {
   int normalize_input;
   float* part;                    // [B*G][64][512]
   float* asum_part;               // [B*G*4][64]   one partial per CTA of the cluster
-  int flags;                      // experiment switches (IBL_NV_FLAGS)
   unsigned long long* dbg;        // optional [gridDim][64] globaltimer stamps (IBL_NV_DEBUG=1)
 };
 
@@ -242,7 +241,6 @@ netvlad_c4_kernel(const __grid_constant__ CUtensorMap tm_xhi, const __grid_const
           }
           mbar_arrive_expect_tx(a_full, 32768);        // 4 CTAs x 32 px x (128 B hi + 128 B lo)
           mbar_wait_cluster(a_full, i2 & 1);
-          if (a.flags & 4) asm volatile("fence.proxy.async;" ::: "memory");
           tc_fence_after();
           const uint32_t xb = smem_u32(smem + NV4_X + buf * 65536);
 #pragma unroll
@@ -352,7 +350,6 @@ netvlad_c4_kernel(const __grid_constant__ CUtensorMap tm_xhi, const __grid_const
       NV4_STAMP(ds);
       mbar_wait_cluster(p_full, i & 1);
       NV4_STAMP(ds + 1);
-      if (a.flags & 2) asm volatile("fence.proxy.async;" ::: "memory");
       float z[16];
       {
         const uint32_t ex = smem_u32(smem + NV4_EX) + (uint32_t)(pxl * 256 + qq * 64);
@@ -380,10 +377,7 @@ netvlad_c4_kernel(const __grid_constant__ CUtensorMap tm_xhi, const __grid_const
         __syncwarp();
         if (lane == 0) {
 #pragma unroll
-          for (int j = 0; j < 4; ++j) {
-            if (a.flags & 1) mbar_arrive_remote(pe_remote[j] + dep);
-            else mbar_arrive_remote_relaxed(pe_remote[j] + dep);
-          }
+          for (int j = 0; j < 4; ++j) mbar_arrive_remote_relaxed(pe_remote[j] + dep);
         }
       }
       float sum = 0.f;
@@ -486,7 +480,6 @@ int launch_netvlad_c4(const CUtensorMap& mx_hi, const CUtensorMap& mx_lo, const 
   a.B = B; a.S = S; a.T = cdiv(S, 128); a.G = G;
   a.ssq = ssq; a.ssq_parts = ssq_parts; a.normalize_input = normalize_input ? 1 : 0;
   a.part = part; a.asum_part = asum_part;
-  { const char* v = getenv("IBL_NV_FLAGS"); a.flags = v ? atoi(v) : 0; }
   static unsigned long long* dbg_dev = nullptr;
   static const bool dbg_on = [] { const char* v = getenv("IBL_NV_DEBUG"); return v && atoi(v) != 0; }();
   if (dbg_on && !dbg_dev) cudaMalloc(&dbg_dev, 148 * 128 * 8);
