@@ -39,7 +39,7 @@ struct GemmTcArgs {
   long long* cand_i;
 };
 
-constexpr int GT_BM = 128, GT_BK = 64;
+constexpr int GT_BM = 128;
 
 // MC = true: the grid is launched as clusters of two CTAs that walk the same column tiles with adjacent
 // row tiles.  Each CTA fetches only half of every B tile and TMA-multicasts it into both CTAs' shared
