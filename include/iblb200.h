@@ -163,7 +163,7 @@ int ibl_l2dist_topk(ibl_engine* e, const float* q, int m, const float* db, int n
                     int d, int k, int64_t idx_base, float* out_dist, int64_t* out_idx,
                     void* stream);
 /* Per-row top-k of an existing dense matrix dist [m,n] (row stride n): the ranks evaluate_all reads
- * from np.argsort (evaluators.py:143,151-159).  Same ordering rule as ibl_l2dist_topk. */
+ * from np.argsort (evaluators.py:143,151-159).  Same ordering rule as ibl_l2dist_topk.  1 <= k <= 1024. */
 int ibl_topk_rows(ibl_engine* e, const float* dist, int m, int n, int k, float* out_dist,
                   int64_t* out_idx, void* stream);
 /* k-way merge of per-shard candidates (after the NCCL all-gather): cand_* [parts,m,k_in]

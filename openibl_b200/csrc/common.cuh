@@ -4,6 +4,7 @@
 #include <cuda_bf16.h>
 #include <stdint.h>
 #include <stdio.h>
+#include <atomic>
 #include <string>
 
 #include "../../include/iblb200.h"
@@ -37,6 +38,26 @@ void set_last_error(const std::string& s);
   } while (0)
 
 static inline int cdiv(long long a, long long b) { return (int)((a + b - 1) / b); }
+
+// "Done once" flag per CUDA device: function attributes (cudaFuncSetAttribute) and device properties belong
+// to a device, and one process may drive several GPUs (one engine each).  done()/mark() look at the calling
+// thread's current device; setting an attribute twice from two threads is harmless, launching before it
+// is set is not, so mark() comes after the setter.
+struct DeviceOnce {
+  std::atomic<unsigned long long> mask[4];
+  DeviceOnce() { for (auto& m : mask) m.store(0); }
+  static int cur() { int d = 0; cudaGetDevice(&d); return d & 255; }
+  bool done() const { const int d = cur(); return (mask[d >> 6].load(std::memory_order_acquire) >> (d & 63)) & 1ull; }
+  void mark() { const int d = cur(); mask[d >> 6].fetch_or(1ull << (d & 63), std::memory_order_release); }
+};
+
+// SM count of the calling thread's current device
+static inline int device_sm_count() {
+  int dev = 0, sms = 0;
+  cudaGetDevice(&dev);
+  if (cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess || sms <= 0) sms = 148;
+  return sms;
+}
 
 // One conv layer of the VGG16 trunk.
 struct ConvLayer {

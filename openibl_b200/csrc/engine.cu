@@ -793,7 +793,7 @@ int ibl_l2dist_topk(ibl_engine* e, const float* q, int m, const float* db, int n
 int ibl_topk_rows(ibl_engine* e, const float* dist, int m, int n, int k, float* out_dist, int64_t* out_idx,
                   void* stream) {
   IBL_REQUIRE(e && dist && out_dist && out_idx, "null argument");
-  IBL_REQUIRE(m >= 0 && n >= 1 && k >= 1 && k <= 128, "bad shape");
+  IBL_REQUIRE(m >= 0 && n >= 1 && k >= 1 && k <= 1024, "bad shape (ibl_topk_rows: 1 <= k <= 1024)");
   DeviceGuard g(e->device);
   e->launches++;
   return launch_topk_rows(dist, n, m, n, k, 0, out_dist, out_idx, false, S(stream));

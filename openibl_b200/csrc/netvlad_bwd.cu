@@ -269,10 +269,10 @@ int launch_netvlad_backward(const float* x, bool nhwc, int N, int C, int S, cons
   nv_bwd_dz_kernel<<<g1, 256, 0, s>>>(f, nhwc, C, S, g, centroids, assign, invnorm, dz);
   IBL_CUDA_OK(cudaGetLastError());
   const size_t smem = (size_t)(2 * 32 * 65 + 2 * 64 * 65 + 32 * (C + 1)) * sizeof(float);
-  static bool attr_done = false;
-  if (!attr_done) {
+  static DeviceOnce attr_done;   // the attribute is per device
+  if (!attr_done.done()) {
     IBL_CUDA_OK(cudaFuncSetAttribute(nv_bwd_dx_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
-    attr_done = true;
+    attr_done.mark();
   }
   const long long dN = (long long)S * C, dS = nhwc ? C : 1, dC = nhwc ? 1 : S;
   nv_bwd_dx_kernel<<<g1, 256, smem, s>>>(f, nhwc, C, S, g, conv_w, assign, dz, invnorm, normalize_input ? 1 : 0, dx,

@@ -517,193 +517,6 @@ conv3x3_tc_kernel(const __grid_constant__ CUtensorMap tm_xhi, const __grid_const
   }
 }
 
-// ---- conv1_2 (Cin = Cout = 64) on SM pairs with the weights resident in shared memory ----------------
-// The 64-wide layer is bound by shared-memory bandwidth, not by the tensor pipe: per 16-wide K step the one-SM
-// kernel reads 14 KiB of operands and the TMA writes 12 KiB of im2col boxes + weights (26 KiB vs 128 B/clk).
-// Here a pair of CTAs forms a 256-pixel tile (tcgen05.mma.cta_group::2) and all nine taps of the weights stay
-// in shared memory, split so that each SM reads only its half of every B operand:
-//     region X (8 KiB/tap)   CTA 0: W_hi[0:64]     CTA 1: W_lo[0:64]      -> A_hi . [W_hi ; W_lo]   (N = 128)
-//     region Y (4 KiB/tap)   CTA 0: W_hi[0:32]     CTA 1: W_hi[32:64]     -> A_lo . W_hi            (N = 64)
-// Per K step and SM: 11 KiB of operand reads + 8 KiB of TMA fills (the im2col boxes of its own patch).
-// MEASURED: 3.5 ms vs 2.1 ms for the one-SM kernel (the small-N pair MMAs are slow) -> opt-in experiment only.
-constexpr int C64_W_TAP = 12288, C64_W_BYTES = 9 * C64_W_TAP;        // 108 KiB
-constexpr int C64_STAGES = 3, C64_STAGE = 2 * TC_A_BYTES;            // hi | lo box of one tap
-
-__global__ void __launch_bounds__(192, 1)
-conv64_pair_kernel(const __grid_constant__ CUtensorMap tm_xhi, const __grid_constant__ CUtensorMap tm_xlo,
-                   const __grid_constant__ CUtensorMap tm_whi, const __grid_constant__ CUtensorMap tm_wlo,
-                   const ConvTcArgs a) {
-  extern __shared__ __align__(1024) uint8_t smem_raw[];
-  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
-  uint8_t* ring = smem + C64_W_BYTES;
-  uint64_t* bars = reinterpret_cast<uint64_t*>(ring + C64_STAGES * C64_STAGE);
-  uint64_t* full_bar = bars;
-  uint64_t* empty_bar = bars + C64_STAGES;
-  uint64_t* tfull_bar = bars + 2 * C64_STAGES;
-  uint64_t* tempty_bar = bars + 2 * C64_STAGES + 2;
-  uint64_t* w_full = bars + 2 * C64_STAGES + 4;
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 2 * C64_STAGES + 5);
-  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  const uint32_t rank = cluster_ctarank();
-  const bool leader = rank == 0;
-  const int worker = blockIdx.x >> 1, n_workers = gridDim.x >> 1;
-  constexpr uint32_t ACC_COLS = 192;
-
-  if (warp == 0 && lane == 0) {
-    tma_prefetch_desc(&tm_xhi); tma_prefetch_desc(&tm_xlo); tma_prefetch_desc(&tm_whi); tma_prefetch_desc(&tm_wlo);
-    for (int i = 0; i < C64_STAGES; ++i) { mbar_init(&full_bar[i], 2); mbar_init(&empty_bar[i], 1); }
-    mbar_init(&tfull_bar[0], 1); mbar_init(&tfull_bar[1], 1);
-    mbar_init(&tempty_bar[0], 8); mbar_init(&tempty_bar[1], 8);
-    mbar_init(w_full, 2);
-    fence_barrier_init();
-    fence_proxy_async();
-  }
-  if (warp == 1) tmem_alloc_2sm(tmem_slot, 512);
-  tc_fence_before();
-  __syncthreads();
-  cluster_sync_all();
-  tc_fence_after();
-  const uint32_t tmem_base = *tmem_slot;
-  const int TW = 1 << a.tw_log2;
-  const int tiles_per_img = a.tiles_h * a.tiles_w;
-
-  if (warp == 0) {
-    if (lane == 0) {
-      {   // resident weights: 27 boxes of [32 rows][64 ch]
-        const uint32_t lead = mapa_u32(smem_u32(w_full), 0);
-        if (leader) mbar_arrive_expect_tx(w_full, 2 * C64_W_BYTES);
-        else mbar_arrive_remote(lead);
-        const CUtensorMap* mx = leader ? &tm_whi : &tm_wlo;     // region X
-        for (int tap = 0; tap < 9; ++tap) {
-          uint8_t* wt = smem + tap * C64_W_TAP;
-          tma_load_3d_2sm(wt, mx, lead, 0, 0, tap);
-          tma_load_3d_2sm(wt + 4096, mx, lead, 0, 32, tap);
-          tma_load_3d_2sm(wt + 8192, &tm_whi, lead, 0, leader ? 0 : 32, tap);   // region Y
-        }
-      }
-      int stage = 0;
-      uint32_t phase = 0;
-      for (int tile = worker; tile < a.total_tiles; tile += n_workers) {
-        const int pt = 2 * tile + (int)rank;
-        const int img = pt / tiles_per_img;
-        const int rem = pt - img * tiles_per_img;
-        const int h0 = (rem / a.tiles_w) * (TC_BM >> a.tw_log2);
-        const int w0 = (rem % a.tiles_w) * TW;
-        for (int tap = 0; tap < 9; ++tap) {
-          const int kh = tap / 3 - 1, kw = tap % 3 - 1;
-          mbar_wait(&empty_bar[stage], phase ^ 1);
-          uint8_t* st = ring + stage * C64_STAGE;
-          const uint32_t lead_full = mapa_u32(smem_u32(&full_bar[stage]), 0);
-          if (leader) mbar_arrive_expect_tx(&full_bar[stage], 2 * C64_STAGE);
-          else mbar_arrive_remote(lead_full);
-          tma_load_4d_2sm(st, &tm_xhi, lead_full, 0, w0 + kw, h0 + kh, img);
-          tma_load_4d_2sm(st + TC_A_BYTES, &tm_xlo, lead_full, 0, w0 + kw, h0 + kh, img);
-          if (++stage == C64_STAGES) { stage = 0; phase ^= 1; }
-        }
-      }
-    }
-  } else if (warp == 1) {
-    if (lane == 0 && leader) {
-      constexpr uint32_t idesc128 = umma_idesc_bf16_f32(256, 128);
-      constexpr uint32_t idesc64 = umma_idesc_bf16_f32(256, 64);
-      mbar_wait(w_full, 0);
-      tc_fence_after();
-      const uint32_t wb = smem_u32(smem);
-      int stage = 0;
-      uint32_t phase = 0;
-      int it = 0;
-      for (int tile = worker; tile < a.total_tiles; tile += n_workers, ++it) {
-        const int as = it & 1;
-        mbar_wait(&tempty_bar[as], ((it >> 1) & 1) ^ 1);
-        tc_fence_after();
-        const uint32_t d_tmem = tmem_base + as * ACC_COLS;
-        for (int tap = 0; tap < 9; ++tap) {
-          mbar_wait(&full_bar[stage], phase);
-          tc_fence_after();
-          const uint32_t sa = smem_u32(ring + stage * C64_STAGE);
-          const uint64_t a_hi = umma_desc_kmajor_sw128(sa), a_lo = umma_desc_kmajor_sw128(sa + TC_A_BYTES);
-          const uint64_t b_x = umma_desc_kmajor_sw128(wb + tap * C64_W_TAP);
-          const uint64_t b_y = umma_desc_kmajor_sw128(wb + tap * C64_W_TAP + 8192);
-#pragma unroll
-          for (int k = 0; k < TC_BK / 16; ++k) {
-            const uint64_t ko = (uint64_t)(k * 2);
-            const uint32_t acc = (tap > 0 || k > 0) ? 1u : 0u;
-            umma_bf16_2sm(d_tmem, a_hi + ko, b_x + ko, idesc128, acc);         // [hi.hi | hi.lo]
-            umma_bf16_2sm(d_tmem + 128, a_lo + ko, b_y + ko, idesc64, acc);    // lo.hi
-          }
-          umma_commit_2sm_mc(&empty_bar[stage], 0x3);
-          if (++stage == C64_STAGES) { stage = 0; phase ^= 1; }
-        }
-        umma_commit_2sm_mc(&tfull_bar[as], 0x3);
-      }
-    }
-  } else {
-    const int q = warp & 3;
-    const int m = q * 32 + lane;
-    const int r = m >> a.tw_log2, c = m & (TW - 1);
-    int it = 0;
-    for (int tile = worker; tile < a.total_tiles; tile += n_workers, ++it) {
-      const int as = it & 1;
-      const int pt = 2 * tile + (int)rank;
-      const int img = pt / tiles_per_img;
-      const int rem = pt - img * tiles_per_img;
-      const int h0 = (rem / a.tiles_w) * (TC_BM >> a.tw_log2);
-      const int w0 = (rem % a.tiles_w) * TW;
-      mbar_wait(&tfull_bar[as], (it >> 1) & 1);
-      tc_fence_after();
-      const uint32_t t_row = tmem_base + ((uint32_t)(q * 32) << 16) + as * ACC_COLS;
-      conv_epilogue_tile<64, true>(a, t_row, img, h0, w0, 0, 0, r, c, TW);
-      tc_fence_before();
-      __syncwarp();
-      if (lane == 0) {
-        if (!leader) mbar_arrive_remote(mapa_u32(smem_u32(&tempty_bar[as]), 0));
-        else mbar_arrive(&tempty_bar[as]);
-      }
-    }
-  }
-  tc_fence_before();
-  __syncthreads();
-  cluster_sync_all();
-  if (warp == 1) { tc_fence_after(); tmem_dealloc_2sm(tmem_base, 512); }
-}
-
-static int launch_conv64_pair(const CUtensorMap& xhi, const CUtensorMap& xlo, const __nv_bfloat16* w_hi,
-                              const __nv_bfloat16* w_lo, const ConvTcArgs& a, cudaStream_t s) {
-  CUtensorMap m_whi, m_wlo;
-  {
-    uint64_t dims[3] = {64, 64, 9};
-    uint64_t str[2] = {64 * 2, 64 * 64 * 2};
-    uint32_t box[3] = {64, 32, 1};
-    IBL_RET(make_tmap(&m_whi, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 3, w_hi, dims, str, box));
-    IBL_RET(make_tmap(&m_wlo, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 3, w_lo, dims, str, box));
-  }
-  constexpr int smem = C64_W_BYTES + C64_STAGES * C64_STAGE + 1024 + 256;
-  static_assert(smem <= 232448, "shared-memory budget");
-  static bool attr_done = false;
-  if (!attr_done) {
-    IBL_CUDA_OK(cudaFuncSetAttribute(conv64_pair_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
-    attr_done = true;
-  }
-  int dev = 0, sms = 148;
-  cudaGetDevice(&dev);
-  cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
-  const int pairs = a.total_tiles < sms / 2 ? a.total_tiles : sms / 2;
-  cudaLaunchConfig_t cfg{};
-  cfg.gridDim = dim3(2 * pairs);
-  cfg.blockDim = dim3(192);
-  cfg.dynamicSmemBytes = smem;
-  cfg.stream = s;
-  cudaLaunchAttribute attr[1];
-  attr[0].id = cudaLaunchAttributeClusterDimension;
-  attr[0].val.clusterDim.x = 2;
-  attr[0].val.clusterDim.y = 1;
-  attr[0].val.clusterDim.z = 1;
-  cfg.attrs = attr;
-  cfg.numAttrs = 1;
-  IBL_CUDA_OK(cudaLaunchKernelEx(&cfg, conv64_pair_kernel, xhi, xlo, m_whi, m_wlo, a));
-  return IBL_OK;
-}
-
 // ---- host launcher --------------------------------------------------------------------------
 template <int BN, int STAGES, bool PAIR, bool HALO = false, int NA = 0>
 static int launch_tc_variant(const CUtensorMap& xhi, const CUtensorMap& xlo, const CUtensorMap& whi,
@@ -711,11 +524,11 @@ static int launch_tc_variant(const CUtensorMap& xhi, const CUtensorMap& xlo, con
   constexpr int smem = ConvTcSmem<BN, PAIR, HALO, NA>::A_RING + STAGES * ConvTcSmem<BN, PAIR, HALO, NA>::STAGE_BYTES +
                        1024 /*align slack*/ + 256 /*barriers*/;
   static_assert(smem <= 232448, "shared-memory budget");
-  static bool attr_done = false;
-  if (!attr_done) {
+  static DeviceOnce attr_done;   // the attribute is per device
+  if (!attr_done.done()) {
     IBL_CUDA_OK(cudaFuncSetAttribute(conv3x3_tc_kernel<BN, STAGES, PAIR, HALO, NA>,
                                      cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
-    attr_done = true;
+    attr_done.mark();
   }
   int dev = 0, sms = 148;
   cudaGetDevice(&dev);
@@ -795,13 +608,10 @@ int launch_conv3x3_tc(const __nv_bfloat16* x_hi, const __nv_bfloat16* x_lo, cons
   const long long patches = (long long)N * a.tiles_h * a.tiles_w;
   const bool pair = pair_env && patches >= 2 && ((bn == 256 && cin >= 256) || pair_env == 2) && bn >= 128 &&
                     !(halo && bn != 256);
-  // conv1_2 shape on SM pairs + resident weights (conv64_pair_kernel): correct, but 3.5 ms against 2.1 ms for the
-  // one-SM kernel -- cta_group::2 MMAs only pay off at N = 256 (N = 64/128 pair MMAs run at about half rate,
-  // same finding as the 128-wide pair variant above).  Opt-in: IBL_CONV64_PAIR=1.
-  static const bool c64_env = [] { const char* v = getenv("IBL_CONV64_PAIR"); return v && atoi(v) != 0; }();
-  const bool c64pair = c64_env && bn == 64 && cin == 64 && cout == 64 && patches >= 2 && !halo;
+  // (A conv1_2 variant on SM pairs with resident weights was measured at 3.5 ms against 2.1 ms for the one-SM
+  // kernel -- cta_group::2 MMAs only pay off at N = 256 -- and was removed; see git history, round 1.)
   a.n_tiles = cout / bn;
-  a.total_tiles = (int)(((pair || c64pair) ? (patches + 1) / 2 : patches) * a.n_tiles);
+  a.total_tiles = (int)((pair ? (patches + 1) / 2 : patches) * a.n_tiles);
   a.relu = relu; a.pool = pool;
   a.bias = p.bias; a.y_hi = y_hi; a.y_lo = y_lo; a.y_f32 = y_f32;
   a.ssq = pool ? nullptr : ssq;
@@ -823,7 +633,6 @@ int launch_conv3x3_tc(const __nv_bfloat16* x_hi, const __nv_bfloat16* x_lo, cons
     IBL_RET(make_tmap(&m_whi, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 3, p.w_hi, dims, str, box));
     IBL_RET(make_tmap(&m_wlo, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 3, p.w_lo, dims, str, box));
   }
-  if (c64pair) return launch_conv64_pair(m_xhi, m_xlo, p.w_hi, p.w_lo, a, s);
   if (halo) {
     if (bn == 64) return launch_tc_variant<64, 4, false, true, 3>(m_xhi, m_xlo, m_whi, m_wlo, a, s);
     if (bn == 128) return launch_tc_variant<128, 3, false, true, 2>(m_xhi, m_xlo, m_whi, m_wlo, a, s);

@@ -234,10 +234,10 @@ int launch_conv1_1_tc(const float* x_nchw, const float* w_oihw, const float* bia
   const long long M = (long long)N * H * W;
   a.total_tiles = (int)((M + 127) / 128);
   const int smem = 16384 + 4 * C1_ABYTES + 1024 + 512 + 4 * 8192;
-  static bool attr_done = false;
-  if (!attr_done) {
+  static DeviceOnce attr_done;   // the attribute is per device
+  if (!attr_done.done()) {
     IBL_CUDA_OK(cudaFuncSetAttribute(conv1_1_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
-    attr_done = true;
+    attr_done.mark();
   }
   int sms = 148, dev = 0;
   cudaGetDevice(&dev);

@@ -285,25 +285,16 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tm_ahi, const __grid_constant
 }
 
 // ---- host ------------------------------------------------------------------------------------
-static int sm_count() {
-  static int sms = 0;
-  if (!sms) {
-    int dev = 0;
-    cudaGetDevice(&dev);
-    cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
-    if (sms <= 0) sms = 148;
-  }
-  return sms;
-}
+static int sm_count() { return device_sm_count(); }   // per device: one process may drive several GPUs
 
 template <int BN, int STAGES, int EPI, bool MC = false, int BK = 64>
 static int launch_gemm_variant(const CUtensorMap* maps, const GemmTcArgs& g, cudaStream_t s) {
   constexpr int smem = STAGES * (2 * GT_BM * BK * 2 + 2 * BN * BK * 2) + 1024 + 256;
-  static bool attr_done = false;
-  if (!attr_done) {
+  static DeviceOnce attr_done;   // the attribute is per device
+  if (!attr_done.done()) {
     IBL_CUDA_OK(cudaFuncSetAttribute(gemm_tc_kernel<BN, STAGES, EPI, MC, BK>,
                                      cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
-    attr_done = true;
+    attr_done.mark();
   }
   if (!MC) {
     const int grid = g.total_items < sm_count() ? g.total_items : sm_count();
@@ -562,10 +553,10 @@ int launch_rescore_sort(const float* q, const float* qn, int m, const float* db,
                         long long* out_idx, cudaStream_t s) {
   IBL_REQUIRE(kc >= 1 && kc <= 128 && k_out >= 1 && k_out <= 128, "rescore: 1 <= k <= 128");
   IBL_REQUIRE(d % 4 == 0, "rescore: dim must be a multiple of 4");
-  static bool attr_done = false;
-  if (!attr_done) {
+  static DeviceOnce attr_done;   // the attribute is per device
+  if (!attr_done.done()) {
     IBL_CUDA_OK(cudaFuncSetAttribute(rescore_sort_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 64 * 1024));
-    attr_done = true;
+    attr_done.mark();
   }
   if (m == 0) return IBL_OK;
   rescore_sort_kernel<<<m, 128, d <= 16384 ? d * sizeof(float) : 16, s>>>(q, qn, db, dbn, d, cand_i, kc, k_out, idx_base,

@@ -206,16 +206,7 @@ gemm2_top16_kernel(const __grid_constant__ CUtensorMap tm_ahi, const __grid_cons
   }
 }
 
-static int sms2() {
-  static int sms = 0;
-  if (!sms) {
-    int dev = 0;
-    cudaGetDevice(&dev);
-    cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
-    if (sms <= 0) sms = 148;
-  }
-  return sms;
-}
+static int sms2() { return device_sm_count(); }   // per device: one process may drive several GPUs
 
 static int pick_runs2(int m_pairs, int n_tiles) {
   const int G = sms2() / 2;
@@ -260,10 +251,10 @@ int launch_dist_top16_2sm(const __nv_bfloat16* q_hi, const __nv_bfloat16* q_lo, 
   g.an = qn; g.bn = dn; g.cand_d = cand_d; g.cand_i = cand_i;
   *runs_out = g.items_per_mpair;
   const int smem = G2_STAGES * G2_STAGE + 1024 + 256;
-  static bool attr_done = false;
-  if (!attr_done) {
+  static DeviceOnce attr_done;   // the attribute is per device
+  if (!attr_done.done()) {
     IBL_CUDA_OK(cudaFuncSetAttribute(gemm2_top16_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
-    attr_done = true;
+    attr_done.mark();
   }
   const int pairs = sms2() / 2;
   const int units = g.total_items < pairs ? g.total_items : pairs;

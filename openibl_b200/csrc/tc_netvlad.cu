@@ -564,22 +564,12 @@ netvlad_finalize_l2_kernel(float* __restrict__ vlad_norm, const float* __restric
   }
 }
 
-// tc_netvlad4.cu: the 4-CTA-cluster kernel.  Opt-in (IBL_NV_CLUSTER=1): it is correct (same parity tests) and
-// reads every feature byte once, but measures 62-77 us against 44 us for the one-SM kernel above at B=32 --
-// the two DSMEM exchanges per tile (48 KiB out per CTA at ~20 B/clk) plus their round trips sit on the
-// critical path and two x buffers are not enough to hide them (profiles/README.md).
-int netvlad_c4_units(int B, int S);
-int launch_netvlad_c4(const CUtensorMap& mx_hi, const CUtensorMap& mx_lo, const CUtensorMap& mw_hi,
-                      const CUtensorMap& mw_lo, int B, int S, int G, const float* ssq, int ssq_parts,
-                      bool normalize_input, float* part, float* asum_part, cudaStream_t s);
-static bool nv_cluster() {
-  static const bool on = [] { const char* v = getenv("IBL_NV_CLUSTER"); return v && atoi(v) != 0; }();
-  return on;
-}
-int netvlad_tc_asum_parts(int G) { return nv_cluster() ? 4 * G : G; }
+// (A 4-CTA-cluster variant that reads every feature byte once -- channels split over the cluster, partial logits
+// reduce-scattered and a' all-gathered through DSMEM -- was parity-green but measured 62-77 us against 35 us for
+// this kernel and was removed from the product library; see git history, round 1: tc_netvlad4.cu.)
+int netvlad_tc_asum_parts(int G) { return G; }
 
 int netvlad_tc_units(int B, int S) {
-  if (nv_cluster()) return netvlad_c4_units(B, S);
   int sms = 148;
   int dev = 0;
   cudaGetDevice(&dev);
@@ -622,24 +612,19 @@ int launch_netvlad_tc(const __nv_bfloat16* x_hi, const __nv_bfloat16* x_lo, int 
   if (dbg_on) cudaMemsetAsync(dbg_dev, 0, 148 * 32 * 8, s);
   a.dbg = dbg_on ? dbg_dev : nullptr;
   const int smem = NV_NSTAGE * NV_STAGE + 2 * NV_SLOT + 1024 + 128 + 4 * 64 * 4;
-  static bool attr_done = false;
-  if (!attr_done) {
+  static DeviceOnce attr_done;   // the attribute is per device
+  if (!attr_done.done()) {
     IBL_CUDA_OK(cudaFuncSetAttribute(netvlad_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
-    attr_done = true;
+    attr_done.mark();
   }
   int sms = 148, dev = 0;
   cudaGetDevice(&dev);
   cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
   const int units = B * a.G;
   const int AG = netvlad_tc_asum_parts(a.G);
-  if (nv_cluster()) {
-    IBL_RET(launch_netvlad_c4(mx_hi, mx_lo, mw_hi, mw_lo, B, S, a.G, ssq, ssq_parts, normalize_input, part,
-                              asum_part, s));
-  } else {
-    netvlad_tc_kernel<<<units < sms ? units : sms, 192, smem, s>>>(mx_hi, mx_lo, mw_hi, mw_lo, a);
-    IBL_CUDA_OK(cudaGetLastError());
-  }
-  if (dbg_on && !nv_cluster()) {   // print phase stamps of a few CTAs (ns relative to the earliest stamp)
+  netvlad_tc_kernel<<<units < sms ? units : sms, 192, smem, s>>>(mx_hi, mx_lo, mw_hi, mw_lo, a);
+  IBL_CUDA_OK(cudaGetLastError());
+  if (dbg_on) {   // print phase stamps of a few CTAs (ns relative to the earliest stamp)
     cudaStreamSynchronize(s);
     static unsigned long long h[148 * 32];
     cudaMemcpy(h, dbg_dev, sizeof(h), cudaMemcpyDeviceToHost);

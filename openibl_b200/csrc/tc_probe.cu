@@ -92,10 +92,10 @@ int debug_umma_strided(const void* A, int rows, const void* B, int s0, int group
     IBL_RET(make_tmap(&mb, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, B, dims, str, box));
   }
   const int smem = 32768 + 8192 + 1024 + 64;
-  static bool attr_done = false;
-  if (!attr_done) {
+  static DeviceOnce attr_done;   // the attribute is per device
+  if (!attr_done.done()) {
     IBL_CUDA_OK(cudaFuncSetAttribute(umma_strided_probe_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
-    attr_done = true;
+    attr_done.mark();
   }
   umma_strided_probe_kernel<<<1, 128, smem, s>>>(ma, mb, rows, s0, group_rows, base_mode, D);
   IBL_CUDA_OK(cudaGetLastError());

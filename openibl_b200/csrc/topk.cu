@@ -13,11 +13,10 @@ __device__ __forceinline__ float orderable_f32(uint32_t u) {
   return __uint_as_float((u & 0x80000000u) ? (u & 0x7fffffffu) : ~u);
 }
 
-constexpr int TK_CAP = 2048;      // candidate buffer (keys)
 constexpr int TK_PER_ITER = 1024; // elements examined per block iteration (4 per thread)
 constexpr unsigned long long TK_MAX = ~0ull;
 
-// in-place ascending bitonic sort of TK_CAP u64 keys in shared memory, 256 threads
+// in-place ascending bitonic sort of n u64 keys in shared memory, 256 threads
 __device__ void bitonic_sort_u64(unsigned long long* buf, int n /*power of two*/) {
   for (int size = 2; size <= n; size <<= 1) {
     for (int stride = size >> 1; stride > 0; stride >>= 1) {
@@ -34,17 +33,21 @@ __device__ void bitonic_sort_u64(unsigned long long* buf, int n /*power of two*/
   __syncthreads();
 }
 
-// one block per query row
+// One block per query row.  buf[0,k) holds the best k keys found so far (after a compaction), buf[k, k+cnt)
+// the candidates appended since.  CAP = 2048 serves k <= 128, CAP = 4096 serves k <= 1024 (the reference's
+// evaluate_all accepts any recall_topk, evaluators.py:142-153).  Invariant before every iteration:
+// k + cnt + TK_PER_ITER <= CAP.
+template <int CAP>
 __global__ void __launch_bounds__(256)
 topk_rows_kernel(const float* __restrict__ dist, long long ld, int n_valid, int k,
                  long long idx_base, float* __restrict__ out_dist,
                  long long* __restrict__ out_idx) {
-  __shared__ unsigned long long buf[TK_CAP];
+  __shared__ unsigned long long buf[CAP];
   __shared__ int cnt;
   __shared__ unsigned long long thr_s;
   const long long row = blockIdx.x;
   const float* d = dist + row * ld;
-  for (int i = threadIdx.x; i < TK_CAP; i += blockDim.x) buf[i] = TK_MAX;
+  for (int i = threadIdx.x; i < CAP; i += blockDim.x) buf[i] = TK_MAX;
   if (threadIdx.x == 0) { cnt = 0; thr_s = TK_MAX; }
   __syncthreads();
 
@@ -58,19 +61,23 @@ topk_rows_kernel(const float* __restrict__ dist, long long ld, int n_valid, int 
             ((unsigned long long)f32_orderable(__ldg(d + j)) << 32) | (unsigned)j;
         if (key < thr) {
           const int pos = atomicAdd(&cnt, 1);
-          buf[k + pos] = key;   // k + cnt <= k + 896 + 1024 <= 2048
+          buf[k + pos] = key;
         }
       }
     }
     __syncthreads();
-    if (cnt > TK_CAP - 128 - TK_PER_ITER) {   // uniform: cnt is shared
-      bitonic_sort_u64(buf, TK_CAP);
-      for (int i = k + threadIdx.x; i < TK_CAP; i += blockDim.x) buf[i] = TK_MAX;
+    // Every thread takes the SAME snapshot of cnt, and nobody starts the next iteration's atomicAdd before
+    // all have read it: the branch below contains barriers, so it must be block-uniform.
+    const int c = cnt;
+    __syncthreads();
+    if (k + c + TK_PER_ITER > CAP) {
+      bitonic_sort_u64(buf, CAP);
+      for (int i = k + threadIdx.x; i < CAP; i += blockDim.x) buf[i] = TK_MAX;
       if (threadIdx.x == 0) { cnt = 0; thr_s = buf[k - 1]; }
       __syncthreads();
     }
   }
-  bitonic_sort_u64(buf, TK_CAP);
+  bitonic_sort_u64(buf, CAP);
   for (int i = threadIdx.x; i < k; i += blockDim.x) {
     const unsigned long long key = buf[i];
     if (key == TK_MAX) {
@@ -86,10 +93,14 @@ topk_rows_kernel(const float* __restrict__ dist, long long ld, int n_valid, int 
 int launch_topk_rows(const float* dist, long long ld, int m, int n_valid, int k, int64_t idx_base,
                      float* out_dist, int64_t* out_idx, bool accumulate, cudaStream_t s) {
   (void)accumulate;
-  IBL_REQUIRE(k >= 1 && k <= 128, "top-k supports 1 <= k <= 128");
+  IBL_REQUIRE(k >= 1 && k <= 1024, "top-k supports 1 <= k <= 1024");
   if (m == 0) return IBL_OK;
-  topk_rows_kernel<<<m, 256, 0, s>>>(dist, ld, n_valid, k, (long long)idx_base, out_dist,
-                                     reinterpret_cast<long long*>(out_idx));
+  if (k <= 128)
+    topk_rows_kernel<2048><<<m, 256, 0, s>>>(dist, ld, n_valid, k, (long long)idx_base, out_dist,
+                                             reinterpret_cast<long long*>(out_idx));
+  else
+    topk_rows_kernel<4096><<<m, 256, 0, s>>>(dist, ld, n_valid, k, (long long)idx_base, out_dist,
+                                             reinterpret_cast<long long*>(out_idx));
   IBL_CUDA_OK(cudaGetLastError());
   return IBL_OK;
 }
@@ -147,11 +158,11 @@ int launch_topk_merge(const float* cand_dist, const int64_t* cand_idx, int parts
   int cap = 2;
   while (cap < total) cap <<= 1;
   const size_t smem = (size_t)cap * (sizeof(long long) + sizeof(uint32_t));
-  static bool attr_set = false;
-  if (!attr_set) {
+  static DeviceOnce attr_set;   // the attribute is per device
+  if (!attr_set.done()) {
     IBL_CUDA_OK(cudaFuncSetAttribute(topk_merge_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                      8192 * 12));
-    attr_set = true;
+    attr_set.mark();
   }
   if (m == 0) return IBL_OK;
   topk_merge_kernel<<<m, 256, smem, s>>>(cand_dist, reinterpret_cast<const long long*>(cand_idx),

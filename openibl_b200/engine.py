@@ -15,6 +15,17 @@ from ._cabi import CONV_SIMT_FP32, CONV_TC_BF16X3, OUT_PCA, OUT_POOL, OUT_VLAD, 
 _engines = {}
 
 
+def invalidate_caches() -> None:
+    """Forget the re-laid-out VGG16 / PCA parameters cached by every engine of this process.
+
+    The cache key is (data_ptr, Tensor._version).  In-place writes through `.data` (EMA / mean-teacher
+    updates, the reference's own `_init_params`, netvlad.py:41-42) do not bump `_version`, so code that
+    mutates parameters that way must call this (the model mirror does so from `_init_params`,
+    `load_state_dict` and `reset_params`, and re-binds on every forward in training mode)."""
+    for eng in _engines.values():
+        eng.invalidate()
+
+
 def _require_cuda(t: torch.Tensor, name: str, dtype=torch.float32) -> torch.Tensor:
     if not isinstance(t, torch.Tensor):
         raise TypeError(f"{name} must be a torch.Tensor")
@@ -47,6 +58,7 @@ class Engine:
         check(self.lib.ibl_engine_create(self.device, byref(h)), "ibl_engine_create")
         self.h = h
         self._vgg_key = None
+        self._pca_key = None
         self._keep = {}
 
     @staticmethod
@@ -95,11 +107,17 @@ class Engine:
         return c.value
 
     # ---- parameters ----------------------------------------------------------------------
-    def set_vgg16(self, weights: Sequence[torch.Tensor], biases: Sequence[torch.Tensor]) -> None:
+    def invalidate(self) -> None:
+        """Drop the (address, version) keys: the next set_vgg16 / set_pca re-lays the parameters out."""
+        self._vgg_key = None
+        self._pca_key = None
+
+    def set_vgg16(self, weights: Sequence[torch.Tensor], biases: Sequence[torch.Tensor], force: bool = False) -> None:
         assert len(weights) == 13 and len(biases) == 13
         key = tuple((w.data_ptr(), w._version, b.data_ptr(), b._version) for w, b in zip(weights, biases))
-        if key == self._vgg_key:
+        if key == self._vgg_key and not force:
             return
+        self._vgg_key = None
         ws = [_require_cuda(w.detach(), "vgg weight") for w in weights]
         bs = [_require_cuda(b.detach(), "vgg bias") for b in biases]
         wa = (c_void_p * 13)(*[w.data_ptr() for w in ws])
@@ -117,17 +135,18 @@ class Engine:
         check(self.lib.ibl_engine_set_netvlad(self.h, _ptr(w), _ptr(c), K, C, _stream(self.device)),
               "ibl_engine_set_netvlad")
 
-    def set_pca(self, weight: torch.Tensor, bias: torch.Tensor) -> None:
+    def set_pca(self, weight: torch.Tensor, bias: torch.Tensor, force: bool = False) -> None:
         key = (weight.data_ptr(), weight._version, bias.data_ptr(), bias._version)
-        if key == getattr(self, "_pca_key", None):
+        if key == self._pca_key and not force:
             return
-        self._pca_key = key
+        self._pca_key = None                      # stays unset if validation or the C call fails
         P = weight.shape[0]
         w = _require_cuda(weight.detach().reshape(P, -1), "pca weight")
         b = _require_cuda(bias.detach().reshape(-1), "pca bias")
-        self._keep["pca"] = (w, b)
         check(self.lib.ibl_engine_set_pca(self.h, _ptr(w), _ptr(b), P, w.shape[1], _stream(self.device)),
               "ibl_engine_set_pca")
+        self._keep["pca"] = (weight, bias, w, b)   # the originals too: their addresses are in the key
+        self._pca_key = key
 
     # ---- stages --------------------------------------------------------------------------
     def vgg16_forward(self, x: torch.Tensor, want_nchw=True, want_pool=True, want_nhwc=False):

@@ -147,10 +147,14 @@ def evaluate_all(distmat, gt, gallery, recall_topk=[1, 5, 10], nms=False):
     k = max(recall_topk) * (12 if nms else 1)
     d = _to_torch(distmat).float()
     eng = Engine.get()
-    order = torch.empty(d.shape[0], 0, dtype=torch.int64)
+    k = min(k, d.shape[1])
+    if k > 1024:
+        # the reference argsorts the whole row and so accepts any recall_topk; the selection kernel keeps
+        # up to 1024 ranks per query (Tokyo nms needs 120) -- fail loudly rather than score an empty ranking
+        raise NotImplementedError(
+            f"evaluate_all needs the first {k} ranks per query; ibl_topk_rows supports at most 1024")
     d = d.to(torch.device("cuda", eng.device))
-    if k <= 128:
-        _, order = eng.topk_rows(d, min(k, d.shape[1]))
+    _, order = eng.topk_rows(d, k)
     order = order.cpu().numpy()
     recalls = recalls_from_topk(order, gt, gallery, recall_topk, nms)
     if rank == 0:

@@ -14,7 +14,7 @@ from __future__ import annotations
 import torch
 from torch import nn
 
-from .engine import Engine
+from .engine import Engine, invalidate_caches
 from .synth import VGG16_PLAN
 
 __all__ = ["VGG", "vgg16", "NetVLAD", "EmbedNet", "EmbedNetPCA", "EmbedRegionNet", "create", "names"]
@@ -53,6 +53,7 @@ class VGG(nn.Module):
                 layers.append(nn.ReLU(inplace=True))
         self.base = nn.Sequential(*layers[:-1])  # no ReLU after conv5_3 (vgg.py:41-42)
         self.gap = nn.AdaptiveMaxPool2d(1)
+        self.register_load_state_dict_post_hook(lambda module, incompatible: invalidate_caches())
         if pretrained:
             self._load_imagenet()
         self._init_params()
@@ -79,6 +80,7 @@ class VGG(nn.Module):
         if self.matconvnet is not None:
             self.base.load_state_dict(torch.load(self.matconvnet))
             self.pretrained = True
+        invalidate_caches()
 
     def reset_params(self):
         for m in self.modules():
@@ -86,6 +88,7 @@ class VGG(nn.Module):
                 nn.init.kaiming_normal_(m.weight, mode="fan_out")
                 if m.bias is not None:
                     nn.init.constant_(m.bias, 0)
+        invalidate_caches()
 
     def conv_params(self):
         convs = [m for m in self.base if isinstance(m, nn.Conv2d)]
@@ -94,7 +97,9 @@ class VGG(nn.Module):
     def _bind(self, x: torch.Tensor) -> Engine:
         eng = Engine.get(x.device)
         ws, bs = self.conv_params()
-        eng.set_vgg16(ws, bs)
+        # training mode: parameters change every step, possibly through `.data` (no version bump) -> always
+        # re-lay them out (25 us of device time); eval mode trusts the (address, version) key
+        eng.set_vgg16(ws, bs, force=self.training and any(w.requires_grad for w in ws))
         return eng
 
     def forward(self, x):
@@ -134,6 +139,7 @@ class NetVLAD(nn.Module):
         self.alpha = (-np.log(0.01) / np.mean(top2[0] - top2[1])).item()
         self.centroids.data.copy_(torch.from_numpy(self.clsts))
         self.conv.weight.data.copy_(torch.from_numpy(self.alpha * assign).unsqueeze(2).unsqueeze(3))
+        invalidate_caches()
 
     def forward(self, x):
         if torch.is_grad_enabled() and (x.requires_grad or self.conv.weight.requires_grad or self.centroids.requires_grad):
@@ -172,6 +178,9 @@ class _EmbedBase(nn.Module):
         super().__init__()
         self.base_model = base_model
         self.net_vlad = net_vlad
+        # load_state_dict copies with Tensor.copy_ (bumps the version) but be explicit: a freshly loaded
+        # checkpoint must never be served from stale re-laid-out weights
+        self.register_load_state_dict_post_hook(lambda module, incompatible: invalidate_caches())
 
     def _init_params(self):
         self.base_model._init_params()

@@ -1,7 +1,6 @@
 """Kernel variants that are selected by environment variables (read once per process) are exercised in child
 processes, each running the relevant subset of the parity tests: every staging / pairing mode of the tcgen05
-conv, the one-SM distance kernel, and the 4-CTA-cluster NetVLAD kernel must give the same answers as the
-defaults.  Also pins the hardware property the halo-staged conv relies on."""
+conv and the one-SM distance kernel must give the same answers as the defaults.  Also pins the hardware property the halo-staged conv relies on."""
 import os
 import subprocess
 import sys
@@ -16,11 +15,9 @@ VARIANTS = [
     ({"IBL_CONV_HALO": "2"}, "conv3x3 or small or odd"),                    # halo staging on every N tile
     ({"IBL_CONV_HALO": "0", "IBL_CONV_2SM": "0"}, "conv3x3 or small or odd"),   # im2col boxes, one SM per tile
     ({"IBL_CONV_2SM": "2", "IBL_CONV_HALO": "0"}, "conv3x3 or odd"),        # SM pairs on the 128-wide tiles too
-    ({"IBL_CONV64_PAIR": "1"}, "conv3x3 or small"),                         # conv1_2 shape on SM pairs, resident weights
     ({"IBL_CONV1_SIMT": "1"}, "small or odd"),                              # CUDA-core conv1_1
     ({"IBL_DIST_2SM": "0"}, "retrieval_vs_reference or topk"),              # one-SM distance kernel
     ({"IBL_DIST_2SM": "0", "IBL_DIST_BN": "128", "IBL_GEMM_MC": "1"}, "retrieval_vs_reference or topk"),
-    ({"IBL_NV_CLUSTER": "1"}, "netvlad_unit or netvlad_ragged or sharp or tokyo"),   # 4-CTA-cluster NetVLAD
 ]
 
 

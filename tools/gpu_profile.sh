@@ -1,7 +1,25 @@
 #!/bin/bash
-# ncu launch list of the bench command + one full capture of the tcgen05 conv kernel (B200_PROFILING.md)
+# One profiling entry point for the GPU box (B200_PROFILING.md).  Run under gpurun from the repo root.
+#   tools/gpu_profile.sh launches [tag]                 ncu launch list (gpu__time_duration) of `bench.py --steps 2`
+#   tools/gpu_profile.sh full <kernel-regex> <tag> [skip] [count] [-- cmd...]
+#                                                       ncu --set full capture of matching kernels; default cmd = bench.py
+# Outputs land in gpurun_out/ (merged back by gpurun); summarise with tools/ncu_summary.py into profiles/.
+set -u
 mkdir -p gpurun_out
-ncu --metrics gpu__time_duration.sum --clock-control none -c 400 --csv --log-file gpurun_out/launches.csv \
-    python bench.py --steps 2 --warmup 1 --no-cpu-baseline > gpurun_out/bench_under_ncu.log 2>&1
-ncu --set full --clock-control none --import-source on -k regex:conv3x3_tc -s 12 -c 3 -f -o gpurun_out/prof_conv_tc \
-    python bench.py --steps 1 --warmup 1 --no-cpu-baseline > gpurun_out/ncu_full.log 2>&1
+mode=${1:-launches}; shift || true
+case "$mode" in
+  launches)
+    tag=${1:-launches}
+    ncu --metrics gpu__time_duration.sum --clock-control none -c 600 --csv --log-file gpurun_out/${tag}.csv \
+        python bench.py --steps 2 --warmup 1 --no-cpu-baseline --no-eager > gpurun_out/${tag}_bench.log 2>&1
+    ;;
+  full)
+    regex=$1; tag=$2; skip=${3:-0}; count=${4:-2}
+    shift 4 2>/dev/null || shift $#
+    if [ "${1:-}" = "--" ]; then shift; fi
+    if [ $# -eq 0 ]; then set -- python bench.py --steps 1 --warmup 1 --no-cpu-baseline --no-eager; fi
+    ncu --set full --clock-control none --import-source on -k regex:${regex} -s ${skip} -c ${count} -f \
+        -o gpurun_out/prof_${tag} "$@" > gpurun_out/ncu_${tag}.log 2>&1
+    ;;
+  *) echo "unknown mode $mode"; exit 2;;
+esac

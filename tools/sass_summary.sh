@@ -1,0 +1,12 @@
+#!/bin/bash
+# Opcode histogram of the product library: the tracked evidence that the hot path is tcgen05 / TMEM / TMA code.
+#   tools/sass_summary.sh > profiles/rNN_sass_summary.txt
+LIB=${1:-openibl_b200/lib/libiblb200.so}
+echo "# cuobjdump -sass $LIB  (sm_100a)  -- Blackwell-specific opcodes per kernel and in total"
+cuobjdump -sass "$LIB" | awk '
+  /Function :/ { fn=$3 }
+  { for (i=1;i<=NF;i++) if ($i ~ /^(UTCHMMA|UTCQMMA|UTCOMMA|UTMALDG|UTMASTG|UTMAPF|LDTM|STTM|UTCBAR|UTCCP|STAS|SYNCS|UBLKCP|UTCATOMSWS|REDAS)/) { op=$i; sub(/;$/,"",op); tot[op]++; per[fn" "op]++ } }
+  END {
+    print "## total"; for (o in tot) printf "%8d  %s\n", tot[o], o | "sort -k2"; close("sort -k2");
+    print "## per kernel"; for (k in per) printf "%8d  %s\n", per[k], k | "sort -k2"; close("sort -k2");
+  }'
