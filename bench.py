@@ -80,18 +80,70 @@ class ClockSampler:
                 "reasons": reasons, "samples": len(sm)}
 
 
-def cpu_reference_images_per_sec(n_images: int, repeats: int = 1):
-    """Reference arithmetic on the host cores: oracle port of EmbedNetPCA.forward."""
-    from oracle import ibl_oracle as O
+def load_conv_traffic():
+    """dram__bytes_read.sum + dram__bytes_write.sum of the 12 conv3x3_tc_kernel launches of one batch-32 step, from
+    the ncu capture committed under profiles/ (per-layer table with layer labels; tools/ncu_conv_traffic.py made it)."""
+    p = os.path.join(ROOT, "profiles", "r02_conv_traffic.json")
+    if not os.path.exists(p):
+        return {"dram_bytes_per_step": None, "note": "no ncu traffic table committed (profiles/r02_conv_traffic.json)"}
+    t = json.load(open(p))
+    return {"dram_bytes_per_step": t["dram_bytes_total"], "vs_algorithmic": t.get("vs_algorithmic"),
+            "note": f"sum over the 12 conv3x3_tc_kernel launches of one step, ncu dram read+write, per-layer table in "
+                    f"profiles/r02_conv_traffic.json / .md ({t.get('captured', 'ncu')})"}
+
+
+def load_json_profile(name):
+    p = os.path.join(ROOT, "profiles", name)
+    return json.load(open(p)) if os.path.exists(p) else {}
+
+
+def cpu_thread_candidates():
+    cores = os.cpu_count() or 1
+    cand = sorted({c for c in (32, 64, 128, cores) if c <= cores}) or [cores]
+    return cand, cores
+
+
+def cpu_reference_setup():
     from openibl_b200 import synth
     sd = synth.make_state_dict(seed=0, with_pca=True)
+    return sd
+
+
+def cpu_pick_threads(sd, probe_images=2):
+    """Sweep the intra-op thread count on a small probe (after one warm-up pass): MKL/oneDNN convs on a 128-core
+    box are often fastest well below the core count, and round 1's fixed 128 threads moved 3.7x box to box."""
+    from oracle import ibl_oracle as O
+    from openibl_b200 import synth
+    x = synth.make_images(seed=1, batch=probe_images)
+    cand, cores = cpu_thread_candidates()
+    best, rates = None, {}
+    with torch.no_grad():
+        for t in cand:
+            torch.set_num_threads(t)
+            O.extract_descriptor(x[:1], sd)                 # warm-up at this thread count
+            t0 = time.perf_counter()
+            O.extract_descriptor(x, sd)
+            rates[t] = probe_images / (time.perf_counter() - t0)
+            if best is None or rates[t] > rates[best]:
+                best = t
+    torch.set_num_threads(best)
+    return best, rates, cores
+
+
+def cpu_reference_images_per_sec(n_images: int, sd=None):
+    """Reference arithmetic on the host cores: oracle port of EmbedNetPCA.forward (evaluators.py:22-34 +
+    netvlad.py:95-110), full warm-up pass, best thread count of the sweep."""
+    from oracle import ibl_oracle as O
+    from openibl_b200 import synth
+    sd = sd or cpu_reference_setup()
+    threads, rates, cores = cpu_pick_threads(sd)
     x = synth.make_images(seed=1, batch=n_images)
     with torch.no_grad():
+        O.extract_descriptor(x, sd)                         # full warm-up pass (allocator, oneDNN primitives)
         t0 = time.perf_counter()
-        for _ in range(repeats):
-            O.extract_descriptor(x, sd)
+        O.extract_descriptor(x, sd)
         dt = time.perf_counter() - t0
-    return n_images * repeats / dt, dt
+    return n_images / dt, dt, threads, rates, cores
 
 
 def cpu_reference_pairs_per_sec(nq: int, ndb: int):
@@ -109,18 +161,19 @@ def run_reference(args):
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return
-    cores = os.cpu_count()
-    torch.set_num_threads(cores)
-    # bounded sample of the batch-32 workload: <= 4 images per step and <= ~64 images in total,
-    # so the whole run stays within a few minutes at ~0.5-1 image/s of CPU throughput
-    per_step = max(1, min(4, 64 // max(args.steps, 1)))
     from oracle import ibl_oracle as O
     from openibl_b200 import synth
-    sd = synth.make_state_dict(seed=0, with_pca=True)          # parameters and inputs are built outside
-    x = synth.make_images(seed=1, batch=per_step)              # the timed region, as on the GPU arm
+    sd = cpu_reference_setup()                                 # parameters and inputs are built outside
+    threads, rates, cores = cpu_pick_threads(sd)               # the timed region, as on the GPU arm
+    # bounded sample of the batch-32 workload: >= 8 images per step unless K steps of that would run past ~5 min
+    rate = rates[threads]
+    per_step = 8
+    if args.steps * per_step / rate > 300.0:
+        per_step = max(2, int(300.0 * rate / max(args.steps, 1)))
+    x = synth.make_images(seed=1, batch=per_step)
     with torch.no_grad():
-        for _ in range(min(args.warmup, 1)):
-            O.extract_descriptor(x[:1], sd)
+        for _ in range(max(1, min(args.warmup, 2))):
+            O.extract_descriptor(x, sd)                        # full warm-up passes
         t0 = time.perf_counter()
         n = 0
         for _ in range(args.steps):
@@ -135,14 +188,54 @@ def run_reference(args):
         "ms_per_step": 1000.0 * dt / args.steps, "higher_is_better": True, "scaling": "weak",
         "vs_baseline": None, "dtype": "f32", "data": "synthetic",
         "config": {"workload": "batch-32 3x480x640 VGG16+NetVLAD+PCA(4096) extraction (configs[1])",
-                   "sample": f"{per_step} images per step"},
-        "cpu_baseline": {"value": val, "unit": "images/s", "cores": cores, "kind": "port",
-                         "sample": f"{per_step} images/step x {args.steps} steps of the batch-32 workload"},
+                   "sample": f"{per_step} images per step", "threads": threads,
+                   "thread_sweep_images_per_s": {str(k): round(v, 3) for k, v in rates.items()}},
+        "cpu_baseline": {"value": val, "unit": "images/s", "cores": threads, "host_cores": cores, "kind": "port",
+                         "sample": f"{per_step} images/step x {args.steps} steps of the batch-32 workload, "
+                                   f"best of thread sweep {sorted(rates)}"},
         "e2e": {"value": val, "unit": "images/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "retrieval": {"metric": "query_db_pairs_per_sec", "value": pps, "unit": "pairs/s",
                       "sample": f"400 x {NDB} x {DIM} pairwise_distance + top-{TOPK}"},
     }
     print(json.dumps(line), flush=True)
+
+
+def gpu_eager_images_per_sec(xs, sd_dev, steps=3):
+    """What stock PyTorch gets on the SAME B200 (SURVEY 2.1 'the bar'): the reference forward as
+    eager torch ops on CUDA tensors -- cuDNN convs (cudnn.benchmark=True as examples/test.py:80), cuBLAS GEMMs, ATen
+    normalisations -- batch 32, same inputs and weights.  Two variants: fp32-strict (TF32 off; the arithmetic the
+    1e-4 tolerance is stated against) and torch defaults (cuDNN convs may use TF32).  The NetVLAD aggregation is the
+    oracle's einsum form, which is FASTER than the reference's literal [B,64,512,1200] temporary (netvlad.py:56-59)."""
+    from oracle import ibl_oracle as O
+    import torch.backends.cudnn as cudnn
+    out = {}
+    old = (cudnn.benchmark, cudnn.allow_tf32, torch.backends.cuda.matmul.allow_tf32)
+    cudnn.benchmark = True
+    try:
+        for name, tf32 in (("fp32_strict", False), ("torch_default", None)):
+            if tf32 is not None:
+                cudnn.allow_tf32 = tf32
+                torch.backends.cuda.matmul.allow_tf32 = tf32
+            else:
+                cudnn.allow_tf32, torch.backends.cuda.matmul.allow_tf32 = True, False      # torch 2.11 defaults
+            with torch.no_grad():
+                for i in range(2):
+                    O.extract_descriptor(xs[i % 2], sd_dev)
+                torch.cuda.synchronize()
+                e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+                e0.record()
+                for i in range(steps):
+                    O.extract_descriptor(xs[i % 2], sd_dev)
+                e1.record()
+                torch.cuda.synchronize()
+            out[name] = {"value": BATCH * steps / (e0.elapsed_time(e1) / 1000.0), "unit": "images/s",
+                         "ms_per_step": e0.elapsed_time(e1) / steps}
+    finally:
+        cudnn.benchmark, cudnn.allow_tf32, torch.backends.cuda.matmul.allow_tf32 = old
+        torch.cuda.empty_cache()
+    out["note"] = ("eager torch 2.11 ops (cuDNN/cuBLAS/ATen) through the oracle's functional forward, cudnn.benchmark=True, "
+                   "batch 32, device-resident inputs; library kernels -- a baseline, not the product path")
+    return out
 
 
 def main():
@@ -153,6 +246,11 @@ def main():
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--conv-mode", default="tc", choices=["tc", "simt"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-eager", action="store_true", help="skip the stock-PyTorch (cuDNN) leg")
+    ap.add_argument("--no-strong", action="store_true", help="skip the 250k-image strong-scaling leg")
+    ap.add_argument("--strong-db", type=int, default=250000)
+    ap.add_argument("--strong-budget-s", type=float, default=240.0,
+                    help="skip the strong-scaling leg if its projected extraction time exceeds this")
     args = ap.parse_args()
     if args.impl == "reference":
         return run_reference(args)
@@ -249,11 +347,12 @@ def main():
         conv_gflop += 2.0 * BATCH * lh * lw * 9 * cin * cout / 1e9
         del xin
     ach_k = conv_gflop / conv_ms
+    conv_traffic = load_conv_traffic()
     roofline = {"bound": "tensor", "kernel": "conv3x3_tc_kernel (12 launches: conv1_2..conv5_3, tcgen05 implicit GEMM, bf16x3)",
                 "achieved": ach_k, "peak": pk["bf16_tflops_sustained"], "unit": "TFLOP/s",
                 "frac": ach_k / pk["bf16_tflops_sustained"],
-                "traffic": 601.3e6, "traffic_note": "ncu dram read+write of one representative launch (conv3_2, 256->256 @120x160, "
-                "B=32: 329 MB + 272 MB vs 315 MB of activations in/out + 9 MB weights), profiles/r01_conv256_tc.md",
+                "traffic": conv_traffic.get("dram_bytes_per_step"), "traffic_note": conv_traffic.get("note"),
+                "traffic_vs_algorithmic": conv_traffic.get("vs_algorithmic"),
                 "peak_source": pk["src"] + " bf16 sustained (cuBLAS)",
                 "note": "achieved = algorithmic fp32-grade FLOPs / sum of the 12 launch durations; the bf16x3 split issues "
                         "3 MMA passes per product, so the tensor pipe executes 3x the algorithmic figure (mma_issue_frac)",
@@ -314,7 +413,33 @@ def main():
         dist.all_reduce(r_ms, op=dist.ReduceOp.MAX)
     pairs = NQ * NDB * world / (float(r_ms.item()) / 1000.0)
 
+    # ---- stock PyTorch on the same GPU (cuDNN / cuBLAS eager): rank 0 only -----------------------
+    eager = None
+    if rank == 0 and not args.no_eager:
+        try:
+            eager = gpu_eager_images_per_sec(xs, sd)
+        except Exception as exc:   # a baseline leg must never take the bench line down
+            eager = {"unavailable": repr(exc)[:200]}
+    barrier()
+
+    # ---- configs[3]: 250k-image gallery sharded over the ranks, strong scaling ---------------------
+    strong = None
+    if not args.no_strong:
+        from openibl_b200 import gallery
+        proj = args.strong_db / max(value, 1.0)          # seconds of extraction at the rate just measured (all ranks)
+        if proj > args.strong_budget_s:
+            strong = {"skipped": f"projected extraction time {proj:.0f} s exceeds --strong-budget-s {args.strong_budget_s:.0f}"}
+        else:
+            # warm-up outside the timed region: allocations, NCCL communicator and its first-call setup
+            gallery.run(eng, 2 * BATCH * world, 64, H, W, BATCH, check_exact=False)
+            strong = gallery.run(eng, args.strong_db, NQ, H, W, BATCH, check_exact=False)
+            strong["note"] = ("same 250k-image gallery whatever N (images seeded by global index): topk_index_hash and "
+                              "recalls must be equal across N; total_s is the strong-scaling time (max over ranks)")
+
     if rank == 0:
+        pk_burst = pk["bf16_tflops"]
+        r_alg = 2.0 * NQ * NDB * DIM * world / (float(r_ms.item()) / 1000.0) / 1e12
+        dist_prof = load_json_profile("r02_dist_tensor_pipe.json")
         line = {
             "metric": "images_per_sec_extraction", "value": value, "unit": "images/s", "n_gpus": world,
             "steps": args.steps, "warmup": max(args.warmup, 3), "ms_per_step": ms_total / args.steps,
@@ -334,15 +459,25 @@ def main():
                                "(ibl/utils/data/__init__.py:37-42) runs on the device"},
             "retrieval": {"metric": "query_db_pairs_per_sec", "value": pairs, "unit": "pairs/s",
                           "workload": f"{NQ} q x {NDB} db/GPU x {DIM}-d, top-{TOPK}, sharded + all-gather merge",
-                          "ms": float(r_ms.item()),
-                          "algorithmic_tflops": 2.0 * NQ * NDB * DIM * world / (float(r_ms.item()) / 1000.0) / 1e12},
+                          "ms": float(r_ms.item()), "algorithmic_tflops": r_alg,
+                          "roofline": {"bound": "tensor", "achieved": r_alg / world, "peak": pk_burst, "unit": "TFLOP/s",
+                                       "frac": r_alg / world / pk_burst,
+                                       "peak_source": pk["src"] + " bf16 burst (cuBLAS), kernel timed alone",
+                                       "tensor_pipe_active_pct": dist_prof.get("tensor_pipe_active_pct"),
+                                       "tensor_pipe_source": dist_prof.get("source"),
+                                       "note": "achieved = 2*m*n*d algorithmic FLOP of the whole call (planes + screening "
+                                               "GEMM + merge + exact re-scoring) per GPU / its CUDA-event time"}},
         }
+        if eager is not None:
+            line["gpu_eager"] = eager
+        if strong is not None:
+            line["strong_250k"] = strong
         if not args.no_cpu_baseline and world == 1:
-            cores = os.cpu_count()
-            torch.set_num_threads(cores)
-            v, dt = cpu_reference_images_per_sec(4)
-            line["cpu_baseline"] = {"value": v, "unit": "images/s", "cores": cores, "kind": "port",
-                                    "sample": f"4 of the 32 images of one step, oracle EmbedNetPCA forward, {dt:.1f} s"}
+            v, dt, threads, rates, cores = cpu_reference_images_per_sec(8)
+            line["cpu_baseline"] = {"value": v, "unit": "images/s", "cores": threads, "host_cores": cores, "kind": "port",
+                                    "thread_sweep_images_per_s": {str(k): round(r, 3) for k, r in rates.items()},
+                                    "sample": f"8 of the 32 images of one step after a full warm-up pass, oracle "
+                                              f"EmbedNetPCA forward, {dt:.1f} s, best thread count of the sweep"}
         print(json.dumps(line), flush=True)
     if world > 1:
         dist.destroy_process_group()

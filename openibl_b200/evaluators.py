@@ -11,6 +11,7 @@ Same call signatures and return types, different data flow:
 """
 from __future__ import annotations
 
+import math
 import time
 from collections import OrderedDict
 
@@ -19,6 +20,7 @@ import torch
 import torch.distributed as dist
 
 from .engine import Engine
+from .utils.data.sampler import slice_bounds
 
 __all__ = ["extract_cnn_feature", "extract_features", "pairwise_distance", "spatial_nms",
            "evaluate_all", "recalls_from_topk", "sharded_topk", "Evaluator"]
@@ -50,16 +52,15 @@ def extract_cnn_feature(model, inputs, vlad=True, gpu=None):
     return Engine.get(outputs.device).l2_normalize_rows(outputs)
 
 
-def extract_features(model, data_loader, dataset, print_freq=10, vlad=True, pca=None, gpu=None,
-                     sync_gather=False):
-    """evaluators.py:36-103 -> OrderedDict{fname: CPU FloatTensor[D]} in `dataset` order.
-    The loader yields (imgs, fnames, pids, x, y); rank r holds the r-th contiguous padded slice
-    (DistributedSliceSampler, sampler.py:194-223)."""
+def _extract_local(model, data_loader, print_freq=10, vlad=True, pca=None, gpu=None):
+    """The loop body of extract_features (evaluators.py:51-63) for this rank's slice: returns the descriptors
+    as ONE GPU tensor [n_local, D] in loader order plus the file names the loader yielded.  No per-batch
+    device->host copy and no synchronisation (the reference does `outputs.data.cpu()` every batch, :58)."""
     model.eval()
-    rank, world = _rank_world()
+    rank, _ = _rank_world()
     if pca is not None:
         pca.load(gpu=gpu)
-    feats = []
+    feats, names = [], []
     end = time.time()
     bt_sum = 0.0
     with torch.no_grad():
@@ -67,21 +68,45 @@ def extract_features(model, data_loader, dataset, print_freq=10, vlad=True, pca=
             out = extract_cnn_feature(model, imgs, vlad, gpu=gpu)
             if pca is not None:
                 out = pca.infer(out)
-            feats.append(out)            # stays on the GPU; no per-batch sync
+            feats.append(out)            # stays on the GPU
+            names.extend(fnames)
             bt = time.time() - end
             bt_sum += bt
             end = time.time()
             if (i + 1) % print_freq == 0 and rank == 0:
                 print("Extract Features: [{}/{}]\tTime {:.3f} ({:.3f})".format(
                     i + 1, len(data_loader), bt, bt_sum / (i + 1)))
-    local = torch.cat(feats) if feats else torch.empty(0, 0, device="cuda")
-    if world > 1:
-        parts = [torch.empty_like(local) for _ in range(world)]
-        dist.all_gather(parts, local)
-        allf = torch.cat(parts)
-    else:
-        allf = local
-    allf = allf[: len(dataset)].cpu()      # drop the sampler's wrap-around padding
+    if feats:
+        return torch.cat(feats), names
+    return torch.empty(0, 0, device=torch.device("cuda", torch.cuda.current_device() if gpu is None else gpu)), names
+
+
+def _all_gather_rows(local, per):
+    """[n_local<=per, D] on every rank -> [world*per, D] (rank-major), one NCCL all-gather on device memory."""
+    _, world = _rank_world()
+    if world == 1:
+        return local
+    if local.shape[0] != per:
+        pad = torch.zeros(per, local.shape[1], device=local.device, dtype=local.dtype)
+        pad[: local.shape[0]] = local
+        local = pad
+    out = torch.empty(world * per, local.shape[1], device=local.device, dtype=local.dtype)
+    dist.all_gather_into_tensor(out, local.contiguous())
+    return out
+
+
+def extract_features(model, data_loader, dataset, print_freq=10, vlad=True, pca=None, gpu=None,
+                     sync_gather=False):
+    """evaluators.py:36-103 -> OrderedDict{fname: CPU FloatTensor[D]} in `dataset` order.
+    The loader yields (imgs, fnames, pids, x, y); rank r holds the r-th contiguous padded slice
+    (DistributedSliceSampler, sampler.py:194-223).  This is the dict-returning contract the training
+    callers and examples/test.py's PCA fit need; Evaluator.evaluate does NOT go through it (shard-resident
+    path below)."""
+    local, _ = _extract_local(model, data_loader, print_freq, vlad, pca, gpu)
+    _, world = _rank_world()
+    per = int(math.ceil(len(dataset) * 1.0 / world)) if world > 1 else local.shape[0]
+    allf = _all_gather_rows(local, per)
+    allf = allf[: len(dataset)].cpu()      # drop the sampler's wrap-around padding; ONE device->host copy
     features = OrderedDict()
     for item, row in zip(dataset, allf):
         features[item[0]] = row
@@ -166,11 +191,13 @@ def evaluate_all(distmat, gt, gallery, recall_topk=[1, 5, 10], nms=False):
 
 def sharded_topk(q: torch.Tensor, db_shard: torch.Tensor, k: int, idx_base: int, n_valid: int,
                  _rank_fn=None, _merge_fn=None):
-    """Distance + top-k of all queries against this rank's database slice, ONE all-gather of the
-    [m,k] candidates (dist and idx packed in one int64 tensor), k-way merge.  Returns
-    (dist [m,k], idx [m,k]), identical on every rank.  `_rank_fn` / `_merge_fn` exist only so the
-    gloo CPU test can drive the distributed plumbing without a GPU; the product path is the CUDA
-    engine."""
+    """Distance + top-k of all queries against this rank's database slice, ONE all-gather of the [m,k]
+    candidates, k-way merge.  Returns (dist [m,k], idx [m,k]), identical on every rank.
+
+    The candidates cross NVLink packed as (fp32 distance bits, int32 global index) = 8 bytes each
+    (all_gather_into_tensor into one preallocated buffer: 0.54 MB per rank at 6.8k queries, k = 10).
+    `_rank_fn` / `_merge_fn` exist only so the gloo CPU test can drive the distributed plumbing without a
+    GPU; the product path is the CUDA engine."""
     _, world = _rank_world()
     if _rank_fn is None:
         eng = Engine.get(q.device)
@@ -179,43 +206,93 @@ def sharded_topk(q: torch.Tensor, db_shard: torch.Tensor, k: int, idx_base: int,
     cd, ci = _rank_fn(q, db_shard, k, idx_base, n_valid)
     if world == 1:
         return cd, ci
-    packed = torch.stack([cd.contiguous().view(torch.int32).to(torch.int64), ci])   # [2,m,k] int64
-    gathered = [torch.empty_like(packed) for _ in range(world)]
-    dist.all_gather(gathered, packed)
-    gd = torch.stack([g[0].to(torch.int32).view(torch.float32) for g in gathered])
-    gi = torch.stack([g[1] for g in gathered])
+    if int(idx_base) + int(db_shard.shape[0]) >= 2 ** 31:
+        raise ValueError("sharded_topk packs global indices as int32: the gallery must have < 2^31 rows")
+    m = cd.shape[0]
+    packed = torch.empty(m, k, 2, dtype=torch.int32, device=cd.device)
+    packed[..., 0] = cd.contiguous().view(torch.int32)
+    packed[..., 1] = ci                                   # -1 (no candidate) survives the narrowing
+    gathered = torch.empty(world * m, k, 2, dtype=torch.int32, device=cd.device)   # rank-major concatenation
+    dist.all_gather_into_tensor(gathered, packed)
+    gathered = gathered.view(world, m, k, 2)
+    gd = gathered[..., 0].contiguous().view(torch.float32)
+    gi = gathered[..., 1].to(torch.int64)
     return _merge_fn(gd, gi, k)
 
 
+def _slice_names(items, world, rank):
+    """File names DistributedSliceSampler(items) hands to `rank` (sampler.py:208-219): a contiguous slice of
+    ceil(n/world) items whose tail wraps to the head."""
+    n = len(items)
+    per = int(math.ceil(n * 1.0 / world))
+    return [items[(rank * per + i) % n][0] for i in range(per)] if n else []
+
+
 class Evaluator(object):
-    """evaluators.py:170-201."""
+    """evaluators.py:170-201.
+
+    Data flow when both loaders are given, as examples/test.py does (:127-131): every rank
+    keeps the descriptors of its database slice in the HBM that produced them; only the queries are
+    all-gathered (6.8k x 16 KiB = 111 MB); every rank ranks all queries against its own slice; the [m,k]
+    candidates are all-gathered (8 B each) and merged.  No descriptor is copied to the host and the [m,n]
+    distance matrix is never built.  The reference gathers every descriptor to every rank's host RAM
+    (:76-101) and computes the dense CPU matrix redundantly on all ranks (:116-130)."""
+
+    _rank_fn = None      # test seam (gloo CPU test): stands in for the CUDA distance/top-k and merge kernels
+    _merge_fn = None
 
     def __init__(self, model):
         self.model = model
         self.rank, _ = _rank_world()
+        self.last_stats = {}
+
+    def _resident_inputs(self, query_loader, query, gallery, gallery_loader, vlad, pca, gpu):
+        """-> (all queries [m,D] on this GPU, this rank's database rows [per,D], first global row, valid rows)
+        or None if a loader did not deliver DistributedSliceSampler slices of `query` / `gallery`."""
+        rank, world = _rank_world()
+        q_local, q_names = _extract_local(self.model, query_loader, vlad=vlad, pca=pca, gpu=gpu)
+        db_local, db_names = _extract_local(self.model, gallery_loader, vlad=vlad, pca=pca, gpu=gpu)
+        ok = (q_names == _slice_names(query, world, rank) and db_names == _slice_names(gallery, world, rank))
+        if world > 1:
+            flag = torch.tensor([1 if ok else 0], device=q_local.device)
+            dist.all_reduce(flag, op=dist.ReduceOp.MIN)
+            ok = bool(flag.item())
+        if not ok:
+            return None, (q_local, q_names, db_local, db_names)
+        per_q = int(math.ceil(len(query) * 1.0 / world))
+        x = _all_gather_rows(q_local, per_q)[: len(query)].contiguous()
+        lo, cnt, per = slice_bounds(len(gallery), world, rank)
+        self.last_stats = {"d2h_descriptor_bytes": 0,
+                           "nvlink_bytes": (world - 1) * per_q * q_local.shape[1] * 4 if world > 1 else 0}
+        return (x, db_local, lo, cnt), None
 
     def evaluate(self, query_loader, dataset, query, gallery, ground_truth, gallery_loader=None,
                  vlad=True, pca=None, rerank=False, gpu=None, sync_gather=False, nms=False, rr_topk=25,
                  lambda_value=0):
-        if gallery_loader is not None:
-            features = extract_features(self.model, query_loader, query, vlad=vlad, pca=pca, gpu=gpu,
-                                        sync_gather=sync_gather)
-            features.update(extract_features(self.model, gallery_loader, gallery, vlad=vlad, pca=pca, gpu=gpu,
-                                             sync_gather=sync_gather))
-        else:
-            features = extract_features(self.model, query_loader, dataset, vlad=vlad, pca=pca, gpu=gpu,
-                                        sync_gather=sync_gather)
         rank, world = _rank_world()
-        dev = torch.device("cuda", torch.cuda.current_device() if gpu is None else gpu)
-        x = torch.stack([features[f] for f, _, _, _ in query]).to(dev)
-        n = len(gallery)
-        per = (n + world - 1) // world
-        lo, hi = min(rank * per, n), min((rank + 1) * per, n)
-        shard = torch.zeros(max(per, 1), x.shape[1], device=dev)
-        if hi > lo:
-            shard[: hi - lo] = torch.stack([features[f] for f, _, _, _ in gallery[lo:hi]]).to(dev)
-        k = min(max(10 * (12 if nms else 1), 1), 128)
-        _, idx = sharded_topk(x, shard, k, idx_base=lo, n_valid=hi - lo)
+        k = min(10 * (12 if nms else 1), 128)
+        resident = None
+        if gallery_loader is not None:
+            resident, leftovers = self._resident_inputs(query_loader, query, gallery, gallery_loader, vlad, pca, gpu)
+        if resident is not None:
+            x, shard, lo, cnt = resident
+        else:
+            # generic loaders (one loader over the union, or a custom sampler): gather by file name
+            if gallery_loader is not None:
+                q_local, q_names, db_local, db_names = leftovers
+                features = self._gather_named(q_local, q_names)
+                features.update(self._gather_named(db_local, db_names))
+            else:
+                local, names = _extract_local(self.model, query_loader, vlad=vlad, pca=pca, gpu=gpu)
+                features = self._gather_named(local, names)
+            x = torch.stack([features[f] for f, _, _, _ in query])
+            lo, cnt, per = slice_bounds(len(gallery), world, rank)
+            shard = torch.stack([features[f] for f, _, _, _ in gallery[lo:lo + cnt]]) if cnt else \
+                torch.zeros(1, x.shape[1], device=x.device)
+        dev = x.device
+        _, idx = sharded_topk(x, shard, k, idx_base=lo, n_valid=cnt, _rank_fn=self._rank_fn, _merge_fn=self._merge_fn)
+        if world > 1:
+            self.last_stats["nvlink_bytes"] = self.last_stats.get("nvlink_bytes", 0) + (world - 1) * idx.numel() * 8
         recalls = recalls_from_topk(idx.cpu().numpy(), ground_truth, gallery, (1, 5, 10), nms)
         if self.rank == 0:
             print("Recall Scores:")
@@ -225,9 +302,11 @@ class Evaluator(object):
             return recalls
         # evaluators.py:194-201: k-reciprocal re-ranking needs the dense q-g, q-q and g-g matrices; they are
         # built on the GPU (tcgen05 dense distance tiles) and re-ranked there (utils/rerank.py), rank 0 only,
-        # as in the reference (the other ranks score the original matrix).
+        # as in the reference (the other ranks score the original matrix).  The database rows are gathered
+        # over NVLink (device memory), never through the host.
         eng = Engine.get(dev)
-        y = torch.stack([features[f] for f, _, _, _ in gallery]).to(dev)
+        _, _, per = slice_bounds(len(gallery), world, rank)
+        y = _all_gather_rows(shard[:per] if shard.shape[0] >= per else shard, per)[: len(gallery)].contiguous()
         distmat = eng.l2dist_dense(x, y)
         if self.rank == 0:
             print("Applying re-ranking ...")
@@ -235,3 +314,19 @@ class Evaluator(object):
             distmat = re_ranking(distmat, eng.l2dist_dense(x, x), eng.l2dist_dense(y, y), k1=rr_topk, k2=1,
                                  lambda_value=lambda_value)
         return evaluate_all(distmat, ground_truth, gallery, nms=nms)
+
+    @staticmethod
+    def _gather_named(local, names):
+        """fname -> GPU row for every image any rank extracted (device all-gather; names travel as objects)."""
+        _, world = _rank_world()
+        if world == 1:
+            return {n: r for n, r in zip(names, local)}
+        counts = [None] * world
+        dist.all_gather_object(counts, (len(names), names))
+        per = max(c for c, _ in counts)
+        rows = _all_gather_rows(local, per)
+        out = {}
+        for r, (c, nm) in enumerate(counts):
+            for j in range(c):
+                out.setdefault(nm[j], rows[r * per + j])
+        return out

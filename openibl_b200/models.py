@@ -66,13 +66,23 @@ class VGG(nn.Module):
 
     def _load_imagenet(self):
         # The reference calls torchvision.models.vgg16(pretrained=True) (vgg.py:40), a download.
+        import os
         try:
             import torchvision
             tv = torchvision.models.vgg16(weights="IMAGENET1K_V1")
         except Exception as exc:  # no network on the build / GPU boxes
+            if os.environ.get("IBL_VGG16_RANDOM_INIT_OK") == "1":
+                # explicit opt-in for callers that load a checkpoint right after construction
+                # (examples/test.py:59,97-99 builds models.create('vgg16') and then copies the checkpoint in)
+                import warnings
+                warnings.warn("vgg16(pretrained=True): ImageNet weights unavailable, continuing with random "
+                              "init because IBL_VGG16_RANDOM_INIT_OK=1 -- load a checkpoint before use")
+                self.reset_params()
+                return
             raise RuntimeError(
                 "vgg16(pretrained=True) needs the torchvision ImageNet weights (a download); "
-                "pass pretrained=False and load a checkpoint instead") from exc
+                "pass pretrained=False and load a checkpoint instead, or set IBL_VGG16_RANDOM_INIT_OK=1 if a "
+                "checkpoint is loaded right after construction") from exc
         sd = {k: v for k, v in tv.features.state_dict().items() if int(k.split(".")[0]) <= 28}
         self.base.load_state_dict(sd)
 

@@ -23,6 +23,11 @@ def write_json(obj, fpath):
         json.dump(obj, f, indent=4, separators=(",", ": "))
 
 
+def read_mat(path, key="dbStruct"):
+    from scipy.io import loadmat
+    return loadmat(path)[key].item()
+
+
 def save_checkpoint(state, is_best, fpath="checkpoint.pth.tar"):
     mkdir_if_missing(osp.dirname(fpath))
     torch.save(state, fpath)

@@ -602,3 +602,89 @@ def test_batch_480x640_properties(eng):
     eng.extract_host(x.pin_memory(), out_host, pca=True)
     assert torch.equal(out_host, desc.cpu())
     assert eng.launch_count > 0
+
+
+# ---------------------------------------------------------------------------------------------
+# configs[1] at its real size against the ORACLE (not only self-consistency)
+# ---------------------------------------------------------------------------------------------
+def test_batch32_480x640_vs_oracle_both_conv_modes(eng, O):
+    """The benchmarked shape -- 32 images of 3x480x640 through ibl_extract (VGG16 + NetVLAD + PCA 4096) -- in both
+    conv math modes against oracle.extract_descriptor (reference forward, evaluators.py:22-34 + netvlad.py:95-110)
+    on the host cores.  Per-image relative L2 <= 1e-4 (north star)."""
+    sd = synth.make_state_dict(seed=0, with_pca=True)
+    _bind(eng, sd)
+    x = synth.make_images(seed=1, batch=32)
+    torch.set_num_threads(max(1, min(64, (torch.get_num_threads() or 1))))
+    with torch.no_grad():
+        want = O.extract_descriptor(x, sd).double()
+    xd = x.cuda()
+    for name, mode, _ in _modes():
+        eng.conv_mode = mode
+        got, _ = eng.extract(xd, pca=True)
+        per_image = ((got.cpu().double() - want).norm(dim=1) / want.norm(dim=1))
+        assert float(per_image.max()) < DESC_TOL, (name, float(per_image.max()))
+    # the golden (unmodified reference, batch 1) is image 0 of this batch
+    g = load_golden("hub_480x640")
+    assert rel_l2(got[:1].cpu(), g["desc"]) < DESC_TOL
+
+
+def test_sharp_full_chain_480x640_vs_oracle(eng, O):
+    """_init_params-style NetVLAD parameters (alpha ~ 280) at the REAL size (S = 1200 locations): the case where
+    the bf16x3 representation error of the feature map is amplified most (7e-5 at 64x96).  Raw 32768-d VLAD and
+    PCA'd descriptors, per image, <= 1e-4."""
+    sd = synth.make_state_dict(seed=11, sharp=True, with_pca=True, bias_scale=0.02)
+    _bind(eng, sd)
+    x = synth.make_images(seed=12, batch=4)
+    with torch.no_grad():
+        _, want_v = O.embednet_forward(x, sd)
+        want_p = O.pca_whiten(want_v, sd["pca_layer.weight"], sd["pca_layer.bias"])
+    worst = {}
+    for name, mode, _ in _modes():
+        eng.conv_mode = mode
+        got_v, _ = eng.extract(x.cuda(), pca=False)
+        got_p, _ = eng.extract(x.cuda(), pca=True)
+        ev = ((got_v.cpu().double() - want_v.double()).norm(dim=1) / want_v.double().norm(dim=1)).max().item()
+        ep = ((got_p.cpu().double() - want_p.double()).norm(dim=1) / want_p.double().norm(dim=1)).max().item()
+        worst[name] = (ev, ep)
+        assert ev < DESC_TOL and ep < DESC_TOL, worst
+    print("sharp 480x640 per-image rel-L2 (vlad, pca):", worst)
+    d = O.self_distance(want_v)
+    assert float(d[~torch.eye(4, dtype=torch.bool)].min()) > 1e-3     # the images are distinguishable
+
+
+def test_evaluate_all_large_k_and_engine_cache_invalidation(eng, O):
+    """evaluate_all with recall_topk beyond 128 ranks (advisor finding: used to return zeros silently) and the
+    explicit cache invalidation for `.data` writes that do not bump Tensor._version."""
+    from openibl_b200.evaluators import evaluate_all
+    from openibl_b200.engine import invalidate_caches
+    q, db, gt = synth.make_gallery(n_db=3000, n_q=40, dim=64, sigma=1.5)
+    d = O.pairwise_distance(q, db).numpy()
+    gallery = [("d%05d" % i, i // 2, 0.0, 0.0) for i in range(3000)]
+    gt_list = [np.array([int(t)]) for t in gt]
+    for topk, nms in (([1, 5, 10, 20], True), ([1, 100, 500], False)):
+        want = O.evaluate_all(d, gt_list, [g[1] for g in gallery], recall_topk=tuple(topk), nms=nms)
+        got = evaluate_all(torch.from_numpy(d), gt_list, gallery, recall_topk=topk, nms=nms)
+        assert np.array_equal(got, want), (topk, nms, got, want)
+    dk, ik = eng.topk_rows(torch.from_numpy(d).cuda(), 1000)
+    wd, wi = O.topk_from_distmat(d, 1000)
+    assert np.array_equal(ik.cpu().numpy(), wi)
+    with pytest.raises(NotImplementedError):
+        evaluate_all(torch.from_numpy(d), gt_list, gallery, recall_topk=[2000])
+    # cache invalidation
+    sd = synth.make_state_dict(seed=5, with_pca=True, pca_dim=128, bias_scale=0.05)
+    sdd = _bind(eng, sd)
+    x = synth.make_images(seed=6, batch=1, height=64, width=96).cuda()
+    a, _ = eng.extract(x, pca=True)
+    w0 = sdd["base_model.base.0.weight"]
+    w0.data.mul_(1.5)                                  # no version bump
+    slots = synth.VGG16_CONV_SLOTS
+    ws, bs = [sdd[f"base_model.base.{s}.weight"] for s in slots], [sdd[f"base_model.base.{s}.bias"] for s in slots]
+    invalidate_caches()
+    eng.set_vgg16(ws, bs)
+    b, _ = eng.extract(x, pca=True)
+    assert rel_l2(a.cpu(), b.cpu()) > 1e-4             # the new weights are in effect
+    sd2 = dict(sd)
+    sd2["base_model.base.0.weight"] = sd["base_model.base.0.weight"] * 1.5
+    with torch.no_grad():
+        want = O.embednetpca_forward(x.cpu(), sd2)
+    assert rel_l2(b.cpu(), want) < DESC_TOL

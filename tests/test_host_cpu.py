@@ -148,14 +148,68 @@ def _gloo_worker(rank, world, port, ret):
         dk, ik = sharded_topk(q, shard, 10, idx_base=lo, n_valid=cnt, _rank_fn=rank_fn, _merge_fn=merge_fn)
         full = O.pairwise_distance(q, db).numpy()
         wd, wi = O.topk_from_distmat(full, 10)
-        ret[rank] = bool(np.array_equal(ik.numpy(), wi) and np.allclose(dk.numpy(), wd, atol=1e-6))
+        ok = bool(np.array_equal(ik.numpy(), wi) and np.allclose(dk.numpy(), wd, atol=1e-6))
+
+        # Evaluator.evaluate end to end (shard-resident path): fake descriptors keyed by file name stand in
+        # for the CUDA forward; loaders are DistributedSliceSampler slices like examples/test.py:38-54
+        import openibl_b200.evaluators as E
+        from torch.utils.data import DataLoader
+        from openibl_b200.utils.data.sampler import DistributedSliceSampler
+        query = [("q/%04d.jpg" % i, 2000 + i, 0.0, 0.0) for i in range(q.shape[0])]
+        gallery = [("db/%04d.jpg" % i, i // 2, 0.0, 0.0) for i in range(db.shape[0])]
+        table = {f: r for (f, _, _, _), r in zip(query + gallery, torch.cat([q, db]))}
+
+        class Items(torch.utils.data.Dataset):
+            def __init__(self, items): self.items = items
+            def __len__(self): return len(self.items)
+            def __getitem__(self, i):
+                f, pid, x, y = self.items[i]
+                return torch.zeros(1), f, pid, x, y
+
+        seen = []
+        def fake_feature(model, inputs, vlad=True, gpu=None):
+            names = seen.pop(0)
+            return torch.stack([table[n] for n in names])
+
+        def loader(items, sampler=None):
+            dl = DataLoader(Items(items), batch_size=8, sampler=sampler or DistributedSliceSampler(items), shuffle=False)
+            class Spy:                      # records the batch's file names for the fake forward
+                def __iter__(s):
+                    for b in dl:
+                        seen.append(list(b[1]))
+                        yield b
+                def __len__(s): return len(dl)
+            return Spy()
+
+        E.extract_cnn_feature = fake_feature
+        ev = E.Evaluator(torch.nn.Identity())
+        E.Evaluator._rank_fn, E.Evaluator._merge_fn = staticmethod(rank_fn), staticmethod(merge_fn)
+        gt_list = [np.array([int(t)]) for t in gt]
+        want = O.recalls_from_ranking(O.topk_from_distmat(full, 10)[1], gt_list, [g[1] for g in gallery])
+        got = ev.evaluate(loader(query), None, query, gallery, gt_list, gallery_loader=loader(gallery))
+        ok = ok and np.array_equal(got, want) and ev.last_stats.get("d2h_descriptor_bytes") == 0
+        want_nms = O.recalls_from_ranking(O.topk_from_distmat(full, 120)[1], gt_list, [g[1] for g in gallery], nms=True)
+        got_nms = ev.evaluate(loader(query), None, query, gallery, gt_list, gallery_loader=loader(gallery), nms=True)
+        ok = ok and np.array_equal(got_nms, want_nms)
+        # a loader that does NOT follow the slice layout (every rank sees everything) takes the by-name path
+        dataset = sorted(query + gallery)
+        from torch.utils.data.sampler import SequentialSampler
+        got2 = ev.evaluate(loader(dataset, SequentialSampler(dataset)), dataset, query, gallery, gt_list)
+        ok = ok and np.array_equal(got2, want)
+        rev = list(reversed(gallery))
+        got3 = ev.evaluate(loader(query), None, query, gallery, gt_list,
+                           gallery_loader=loader(rev, DistributedSliceSampler(rev)))
+        ok = ok and np.array_equal(got3, want)
+        ret[rank] = ok
     finally:
         dist.destroy_process_group()
 
 
-def test_sharded_topk_world2_gloo():
+def test_sharded_topk_and_evaluator_world2_gloo():
     """N>1 host logic on CPU: slice the database like DistributedSliceSampler, all-gather the per-shard
-    candidates over gloo, merge; must equal the single-process oracle ranking."""
+    candidates (packed fp32 + int32) over gloo, merge; must equal the single-process oracle ranking.  Then
+    Evaluator.evaluate at world size 2 (shard-resident path, nms path, by-name fallback paths) against the
+    oracle's recalls, with the kernels replaced by the oracle."""
     import torch.multiprocessing as mp
     ctx = mp.get_context("spawn")
     with ctx.Manager() as mgr:
