@@ -93,6 +93,27 @@ int ibl_engine_set_pca(ibl_engine* e, const float* W, const float* b, int P, int
 int ibl_vgg16_forward(ibl_engine* e, const float* x_nchw, int N, int H, int W,
                       float* feat_nhwc, float* feat_nchw, float* pool, void* stream);
 
+/* ---- stage (i), training surface (config 5: SFRS trains conv5_x, vgg.py:50-53) --------------- */
+/* Layers are numbered 0..12 (conv1_1..conv5_3); activations cross the boundary as fp32 NHWC.
+ * Frozen prefix: layers [0, n_layers) with their ReLUs and pools -> out_nhwc (the activation entering layer
+ * n_layers); what autograd skips for requires_grad=False layers (vgg.py:50-53). */
+int ibl_vgg16_prefix_forward(ibl_engine* e, const float* x_nchw, int N, int H, int W, int n_layers,
+                             float* out_nhwc, void* stream);
+/* One trainable layer: y = [ReLU](conv3x3(x) + b), no pooling (vgg.py:61-62 one nn.Conv2d + nn.ReLU).
+ * layer 0 reads the NCHW image, layers >= 1 fp32 NHWC [N,H,W,Cin]; y [N,H,W,Cout]. */
+int ibl_vgg16_layer_forward(ibl_engine* e, int layer, const float* x, int N, int H, int W, float* y_nhwc,
+                            void* stream);
+/* nn.MaxPool2d(2, 2) forward / backward on fp32 NHWC (gradient to the first maximum of each window). */
+int ibl_maxpool2x2_forward(ibl_engine* e, const float* x_nhwc, int N, int H, int W, int C, float* y_nhwc,
+                           void* stream);
+int ibl_maxpool2x2_backward(ibl_engine* e, const float* x_nhwc, const float* gy_nhwc, int N, int H, int W, int C,
+                            float* gx_nhwc, void* stream);
+/* Backward of one trainable layer (what autograd + cuDNN dgrad/wgrad compute for vgg.py:61-62): x = the layer's
+ * input, y = its post-ReLU output (read only if the layer has a ReLU), gy = dL/dy.  gx = dL/dx (NULL for the first
+ * trainable layer), gw [Cout,Cin,3,3], gb [Cout].  dgrad and wgrad run on tcgen05 (bf16x3). */
+int ibl_vgg16_layer_backward(ibl_engine* e, int layer, const float* x, const float* y, const float* gy, int N,
+                             int H, int W, float* gx, float* gw, float* gb, void* stream);
+
 /* ---- stage (ii): NetVLAD --------------------------------------------------- */
 /* NetVLAD.forward (netvlad.py:44-61) + EmbedNet normalisation (netvlad.py:78-80), fused.
  * feat is [N,S,C] if nhwc != 0 else [N,C,S].  conv_w/centroids [K,C] are read directly.
@@ -175,7 +196,15 @@ int ibl_topk_merge(ibl_engine* e, const float* cand_dist, const int64_t* cand_id
 int ibl_l2dist_topk_host(ibl_engine* e, const float* q_host, int m, const float* db_host, int n,
                          int d, int k, float* out_dist_host, int64_t* out_idx_host, void* stream);
 
+/* C[m,n] = alpha * A[m,k] . B[n,k]^T on the engine's GEMM kernels: the products of PCA.train (pca.py:38-67,
+ * torch.matmul there).  mode IBL_CONV_SIMT_FP32 (fp32 CUDA cores) or IBL_CONV_TC_BF16X3 (tcgen05, k % 64 == 0). */
+int ibl_gemm_nt(ibl_engine* e, const float* A, int m, const float* B, int n, int k, float alpha, float* C, int mode,
+                void* stream);
+
 /* ---- self-tests (GPU) ------------------------------------------------------ */
+/* Queries that the guard of the single-pass distance path re-ranked by exact brute force in the last
+ * ibl_l2dist_topk call (-1: that path was not taken).  Synchronises. */
+int ibl_debug_dist_flagged(ibl_engine* e, int* count, void* stream);
 /* Runs the tcgen05/TMA building blocks against CUDA-core results on the device;
  * returns IBL_OK when all agree. max_rel_err (may be NULL) receives the worst error. */
 int ibl_selftest_tc(ibl_engine* e, float* max_rel_err);

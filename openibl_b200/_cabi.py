@@ -33,6 +33,11 @@ SIGNATURES = {
     "ibl_engine_set_netvlad": (c_int, [_P, _P, _P, c_int, c_int, _P]),
     "ibl_engine_set_pca": (c_int, [_P, _P, _P, c_int, c_int, _P]),
     "ibl_vgg16_forward": (c_int, [_P, _P, c_int, c_int, c_int, _P, _P, _P, _P]),
+    "ibl_vgg16_prefix_forward": (c_int, [_P, _P, c_int, c_int, c_int, c_int, _P, _P]),
+    "ibl_vgg16_layer_forward": (c_int, [_P, c_int, _P, c_int, c_int, c_int, _P, _P]),
+    "ibl_maxpool2x2_forward": (c_int, [_P, _P, c_int, c_int, c_int, c_int, _P, _P]),
+    "ibl_maxpool2x2_backward": (c_int, [_P, _P, _P, c_int, c_int, c_int, c_int, _P, _P]),
+    "ibl_vgg16_layer_backward": (c_int, [_P, c_int, _P, _P, _P, c_int, c_int, c_int, _P, _P, _P, _P]),
     "ibl_netvlad_forward": (c_int, [_P, _P, c_int, c_int, c_int, c_int, _P, _P, c_int, c_int, _P, _P, _P]),
     "ibl_netvlad_backward": (c_int, [_P, _P, c_int, c_int, c_int, c_int, _P, _P, c_int, c_int, _P, _P, _P, _P, _P]),
     "ibl_vlad_normalize": (c_int, [_P, _P, c_int, c_int, c_int, _P, _P]),
@@ -48,6 +53,8 @@ SIGNATURES = {
     "ibl_topk_rows": (c_int, [_P, _P, c_int, c_int, c_int, _P, _P, _P]),
     "ibl_topk_merge": (c_int, [_P, _P, _P, c_int, c_int, c_int, c_int, _P, _P, _P]),
     "ibl_l2dist_topk_host": (c_int, [_P, _P, c_int, _P, c_int, c_int, c_int, _P, _P, _P]),
+    "ibl_gemm_nt": (c_int, [_P, _P, c_int, _P, c_int, c_int, c_float, _P, c_int, _P]),
+    "ibl_debug_dist_flagged": (c_int, [_P, POINTER(c_int), _P]),
     "ibl_selftest_tc": (c_int, [_P, POINTER(c_float)]),
     "ibl_debug_gemm_tn": (c_int, [_P, _P, _P, _P, _P]),
     "ibl_debug_umma_strided": (c_int, [_P, _P, c_int, _P, c_int, c_int, c_int, _P, _P]),

@@ -102,19 +102,30 @@ int launch_conv3x3_tc(const __nv_bfloat16* x_hi, const __nv_bfloat16* x_lo, cons
 int launch_maxpool2x2_planes(const __nv_bfloat16* hi, const __nv_bfloat16* lo, int N, int H, int W,
                              int C, __nv_bfloat16* yhi, __nv_bfloat16* ylo, cudaStream_t s);
 int tc_selftest(float* max_rel_err, cudaStream_t s);
+// tc_conv_bwd.cu  (dgrad filter re-layout, tcgen05 wgrad, ReLU mask, pool backward, conv1_1 wgrad)
+int launch_repack_weights_dgrad(const float* w_tck, int cout, int cin, __nv_bfloat16* w_hi, __nv_bfloat16* w_lo,
+                                cudaStream_t s);
+int launch_relu_mask_planes(const float* g, const float* y, size_t n, bool relu, __nv_bfloat16* hi, __nv_bfloat16* lo,
+                            cudaStream_t s);
+int launch_maxpool2x2_bwd(const float* x, const float* gy, int N, int H, int W, int C, float* gx, cudaStream_t s);
+int wgrad_tc_splits(int N, int H, int W, int cin, int cout);
+int launch_conv_wgrad_tc(const __nv_bfloat16* g_hi, const __nv_bfloat16* g_lo, const __nv_bfloat16* x_hi,
+                         const __nv_bfloat16* x_lo, int N, int H, int W, int cin, int cout, float* part, int splits,
+                         float* bpart, float* dw_oihw, float* db, cudaStream_t s);
+int launch_conv1_1_wgrad(const float* x_nchw, const __nv_bfloat16* g_hi, const __nv_bfloat16* g_lo, int N, int H, int W,
+                         float* part, float* dw_oihw, float* db, cudaStream_t s);
 // tc_conv1.cu
 int launch_conv1_1_tc(const float* x_nchw, const float* w_oihw, const float* bias, int N, int H, int W,
                       __nv_bfloat16* y_hi, __nv_bfloat16* y_lo, cudaStream_t s);
 // tc_netvlad.cu
 int debug_gemm_tn(const float* A, const float* B, float* C, cudaStream_t s);
 int netvlad_tc_units(int B, int S);
-int netvlad_tc_asum_parts(int G);   // partials of sum_s a per image the active kernel writes
 // tc_probe.cu
 int debug_umma_strided(const void* A, int rows, const void* B, int s0, int group_rows, int base_mode, float* D,
                        cudaStream_t s);
 int launch_netvlad_tc(const __nv_bfloat16* x_hi, const __nv_bfloat16* x_lo, int B, int S,
                       const __nv_bfloat16* w_hi, const __nv_bfloat16* w_lo, const float* ssq, int ssq_parts,
-                      const float* cent, bool normalize_input, float* part, float* asum_part,
+                      const float* cent, bool normalize_input, float* part, float* asum_part, int* ticket,
                       float* vlad_raw, float* vlad_norm, cudaStream_t s);
 int launch_global_maxpool_planes(const __nv_bfloat16* hi, const __nv_bfloat16* lo, int N, int S, int C, float* y,
                                  cudaStream_t s);
@@ -133,6 +144,11 @@ int dist_top16_2sm_max_runs(int m, int n_valid);
 int launch_dist_top16_2sm(const __nv_bfloat16* q_hi, const __nv_bfloat16* q_lo, const float* qn, int m,
                           const __nv_bfloat16* d_hi, const __nv_bfloat16* d_lo, const float* dn, int n,
                           int n_valid, int K, float* cand_d, long long* cand_i, int* runs_out, cudaStream_t s);
+// tc_dist1.cu  (single-pass fp16 screening on SM pairs + exact re-scoring + guard + exact fallback)
+size_t dist1_workspace_bytes(int m, int n, int d, size_t* off /*[9]*/);
+int launch_dist_topk_1pass(const float* q, int m, const float* db, int n, int n_valid, int d, int k, long long idx_base,
+                           void* ws, float* out_dist, long long* out_idx, uint64_t* launches, cudaStream_t s);
+int dist1_last_flag_count(void* ws, int m, int n, int d, int* out, cudaStream_t s);
 int pca_tc_splits(int P, int D);
 int launch_pca_partial_tc(const __nv_bfloat16* w_hi, const __nv_bfloat16* w_lo, int P,
                           const __nv_bfloat16* v_hi, const __nv_bfloat16* v_lo, int N, int D,

@@ -79,7 +79,11 @@ struct ibl_engine {
   DevBuf q_pl, db_pl, v_pl, pca_pl;     // bf16 hi|lo planes of queries, database shard, descriptors, PCA W
   const float* pca_pl_src = nullptr;    // W pointer the cached planes were made from
   DevBuf mrg_d, mrg_i;
+  DevBuf bw_g, bw_x, bw_part, bw_w;      // conv backward: dY planes, X planes, wgrad/bias partials, dgrad filter planes
+  DevBuf d1_ws;                          // workspace of the single-pass distance/top-k path (tc_dist1.cu)
+  int d1_m = 0, d1_n = 0, d1_d = 0;      // shape of the last call on it (test hook ibl_debug_dist_flagged)
   DevBuf ssq, nv_part, nv_asum, nvw_pl;  // fused NetVLAD: |x|^2 partials, unit partials, W planes [64,512]
+  DevBuf nv_ticket;                      // [images] arrival counters of the fused NetVLAD kernel (zero between launches)
   const float* nvw_pl_src = nullptr;
   cudaStream_t copy_stream = nullptr;   // H2D staging of ibl_extract_host overlaps compute
   cudaEvent_t copy_ev[2] = {nullptr, nullptr};
@@ -108,8 +112,17 @@ struct DeviceGuard {
   }
 };
 
+// arrival counters of the fused NetVLAD kernel: zeroed when (re)allocated, left at zero by every launch
+int ensure_tickets(ibl_engine* e, int n_images, cudaStream_t s) {
+  const size_t need = (size_t)(n_images > 1024 ? n_images : 1024) * sizeof(int);
+  if (e->nv_ticket.cap >= need) return IBL_OK;
+  IBL_RET(e->nv_ticket.ensure(need));
+  IBL_CUDA_OK(cudaMemsetAsync(e->nv_ticket.p, 0, e->nv_ticket.cap, s));
+  return IBL_OK;
+}
+
 int vgg_forward_impl(ibl_engine* e, const float* x, int N, int H, int W, float* feat_nhwc,
-                     cudaStream_t s, FeatPlanes* planes_out = nullptr) {
+                     cudaStream_t s, FeatPlanes* planes_out = nullptr, int last_layer = 12) {
   // largest activation: conv1_x output, N*H*W*64 values of 4 bytes (fp32, or bf16 hi + bf16 lo)
   const size_t act_bytes = (size_t)N * H * W * 64 * 4;
   IBL_RET(e->act[0].ensure(act_bytes));
@@ -119,15 +132,15 @@ int vgg_forward_impl(ibl_engine* e, const float* x, int N, int H, int W, float* 
   if (e->conv_mode == IBL_CONV_SIMT_FP32) {
     IBL_RET(launch_conv1_1(x, e->conv[0], N, h, w, false, e->act[0].as<float>(), nullptr, nullptr, s));
     e->launches++;
-    for (int l = 1; l < 13; ++l) {
+    for (int l = 1; l <= last_layer; ++l) {
       const ConvLayer& L = kVgg16[l];
-      const bool last = (l == 12);
-      float* dst = last ? feat_nhwc : e->act[cur ^ 1].as<float>();
+      const bool last = (l == last_layer);
+      float* dst = (last && !L.pool) ? feat_nhwc : e->act[cur ^ 1].as<float>();
       IBL_RET(launch_conv3x3_simt(e->act[cur].as<float>(), e->conv[l], N, h, w, L.cin, L.cout, L.relu, dst, s));
       e->launches++;
       cur ^= 1;
       if (L.pool) {
-        IBL_RET(launch_maxpool2x2(e->act[cur].as<float>(), N, h, w, L.cout, e->act[cur ^ 1].as<float>(), s));
+        IBL_RET(launch_maxpool2x2(e->act[cur].as<float>(), N, h, w, L.cout, last ? feat_nhwc : e->act[cur ^ 1].as<float>(), s));
         e->launches++;
         cur ^= 1;
         h /= 2;
@@ -149,9 +162,9 @@ int vgg_forward_impl(ibl_engine* e, const float* x, int N, int H, int W, float* 
       IBL_RET(launch_conv1_1_tc(x, e->w0_oihw, e->conv[0].bias, N, h, w, hi_of(0, elems), lo_of(0, elems), s));
   }
   e->launches++;
-  for (int l = 1; l < 13; ++l) {
+  for (int l = 1; l <= last_layer; ++l) {
     const ConvLayer& L = kVgg16[l];
-    const bool last = (l == 12);
+    const bool last = (l == last_layer);
     const size_t in_elems = (size_t)N * h * w * L.cin;
     const int oh = L.pool ? h / 2 : h, ow = L.pool ? w / 2 : w;
     const size_t out_elems = (size_t)N * oh * ow * L.cout;
@@ -236,7 +249,7 @@ int ibl_engine_destroy(ibl_engine* e) {
   DevBuf* bufs[] = {&e->act[0], &e->act[1], &e->feat, &e->nv_assign, &e->nv_inv, &e->nv_raw, &e->vlad,
                     &e->pca_partial, &e->qn, &e->dbn, &e->dist_chunk, &e->cand_d, &e->cand_i,
                     &e->stage_in, &e->stage_out, &e->stage_out2, &e->stage_u8, &e->q_pl, &e->db_pl, &e->v_pl, &e->pca_pl,
-                    &e->mrg_d, &e->mrg_i, &e->ssq, &e->nv_part, &e->nv_asum, &e->nvw_pl};
+                    &e->mrg_d, &e->mrg_i, &e->d1_ws, &e->bw_g, &e->bw_x, &e->bw_part, &e->bw_w, &e->ssq, &e->nv_part, &e->nv_asum, &e->nvw_pl, &e->nv_ticket};
   for (DevBuf* b : bufs) b->release();
   delete e;
   return IBL_OK;
@@ -352,6 +365,118 @@ int ibl_vgg16_forward(ibl_engine* e, const float* x, int N, int H, int W, float*
   return IBL_OK;
 }
 
+// ---- training surface of the trunk: frozen prefix, per-layer forward and backward --------
+// Layers are numbered 0..12 (conv1_1 .. conv5_3).  Activations cross this boundary as fp32 NHWC.
+
+// Frozen prefix: conv layers [0, n_layers) with their ReLUs and pools (inference kernels, nothing saved).
+// out_nhwc: [N, h, w, C] of the activation that enters layer n_layers.
+int ibl_vgg16_prefix_forward(ibl_engine* e, const float* x, int N, int H, int W, int n_layers, float* out_nhwc,
+                             void* stream) {
+  IBL_REQUIRE(e && x && out_nhwc, "null argument");
+  IBL_REQUIRE(n_layers >= 1 && n_layers <= 13, "prefix length must be 1..13");
+  IBL_REQUIRE(N >= 1 && H >= 16 && W >= 16, "VGG16 trunk needs N>=1 and H,W>=16");
+  if (!e->vgg_ready) { set_last_error("ibl_engine_set_vgg16 was not called"); return IBL_ERR_NOT_READY; }
+  DeviceGuard g(e->device);
+  if (n_layers == 1) {
+    e->launches++;
+    return launch_conv1_1(x, e->conv[0], N, H, W, false, out_nhwc, nullptr, nullptr, S(stream));
+  }
+  return vgg_forward_impl(e, x, N, H, W, out_nhwc, S(stream), nullptr, n_layers - 1);
+}
+
+// One trainable layer forward: y = [ReLU](conv(x) + b), NO pooling (the caller pools, so that the pre-pool
+// activation is available to the backward).  layer 0 takes the NCHW image, layers >= 1 fp32 NHWC.
+int ibl_vgg16_layer_forward(ibl_engine* e, int layer, const float* x, int N, int H, int W, float* y_nhwc, void* stream) {
+  IBL_REQUIRE(e && x && y_nhwc, "null argument");
+  IBL_REQUIRE(layer >= 0 && layer < 13 && N >= 1 && H >= 1 && W >= 1, "bad layer / shape");
+  if (!e->vgg_ready) { set_last_error("ibl_engine_set_vgg16 was not called"); return IBL_ERR_NOT_READY; }
+  DeviceGuard g(e->device);
+  cudaStream_t s = S(stream);
+  const ConvLayer& L = kVgg16[layer];
+  if (layer == 0) {
+    e->launches++;
+    return launch_conv1_1(x, e->conv[0], N, H, W, false, y_nhwc, nullptr, nullptr, s);
+  }
+  if (e->conv_mode == IBL_CONV_SIMT_FP32) {
+    e->launches++;
+    return launch_conv3x3_simt(x, e->conv[layer], N, H, W, L.cin, L.cout, L.relu, y_nhwc, s);
+  }
+  const size_t in_e = (size_t)N * H * W * L.cin;
+  IBL_RET(e->act[0].ensure(in_e * 4));
+  __nv_bfloat16* xh = e->act[0].as<__nv_bfloat16>();
+  IBL_RET(launch_f32_to_planes(x, in_e, xh, xh + in_e, s));
+  IBL_RET(launch_conv3x3_tc(xh, xh + in_e, e->conv[layer], N, H, W, L.cin, L.cout, L.relu, false, nullptr, nullptr,
+                            y_nhwc, s));
+  e->launches += 2;
+  return IBL_OK;
+}
+
+int ibl_maxpool2x2_forward(ibl_engine* e, const float* x_nhwc, int N, int H, int W, int C, float* y_nhwc, void* stream) {
+  IBL_REQUIRE(e && x_nhwc && y_nhwc && N >= 1 && H >= 2 && W >= 2 && C >= 4 && C % 4 == 0, "bad argument");
+  DeviceGuard g(e->device);
+  e->launches++;
+  return launch_maxpool2x2(x_nhwc, N, H, W, C, y_nhwc, S(stream));
+}
+
+int ibl_maxpool2x2_backward(ibl_engine* e, const float* x_nhwc, const float* gy_nhwc, int N, int H, int W, int C,
+                            float* gx_nhwc, void* stream) {
+  IBL_REQUIRE(e && x_nhwc && gy_nhwc && gx_nhwc && N >= 1 && H >= 2 && W >= 2 && C >= 1, "bad argument");
+  DeviceGuard g(e->device);
+  e->launches++;
+  return launch_maxpool2x2_bwd(x_nhwc, gy_nhwc, N, H, W, C, gx_nhwc, S(stream));
+}
+
+// Backward of one trainable layer.  x: the layer's input (fp32 NHWC; NCHW image for layer 0), y: its post-ReLU,
+// pre-pool output (only read when the layer has a ReLU), gy: dL/dy.  Outputs: gx (dL/dx, nullable -- not needed for
+// the first trainable layer), gw [Cout,Cin,3,3] (OIHW, the parameter's layout), gb [Cout].
+int ibl_vgg16_layer_backward(ibl_engine* e, int layer, const float* x, const float* y, const float* gy, int N, int H,
+                             int W, float* gx, float* gw, float* gb, void* stream) {
+  IBL_REQUIRE(e && x && gy && gw && gb, "null argument");
+  IBL_REQUIRE(layer >= 0 && layer < 13 && N >= 1 && H >= 1 && W >= 1, "bad layer / shape");
+  if (!e->vgg_ready) { set_last_error("ibl_engine_set_vgg16 was not called"); return IBL_ERR_NOT_READY; }
+  const ConvLayer& L = kVgg16[layer];
+  IBL_REQUIRE(!L.relu || y, "the layer has a ReLU: its output is needed for the mask");
+  DeviceGuard g(e->device);
+  cudaStream_t s = S(stream);
+  const size_t out_e = (size_t)N * H * W * L.cout, in_e = (size_t)N * H * W * L.cin;
+  // dY (after the ReLU mask) as bf16 hi/lo planes: the operand of dgrad, wgrad and the bias gradient
+  IBL_RET(e->bw_g.ensure(out_e * 4));
+  __nv_bfloat16* gh = e->bw_g.as<__nv_bfloat16>();
+  IBL_RET(launch_relu_mask_planes(gy, y, out_e, L.relu, gh, gh + out_e, s));
+  e->launches++;
+  if (layer == 0) {
+    IBL_REQUIRE(!gx, "conv1_1 has no input gradient (its input is the image)");
+    IBL_RET(e->bw_part.ensure((size_t)1024 * 64 * 28 * sizeof(float)));
+    IBL_RET(launch_conv1_1_wgrad(x, gh, gh + out_e, N, H, W, e->bw_part.as<float>(), gw, gb, s));
+    e->launches += 2;
+    return IBL_OK;
+  }
+  IBL_RET(e->bw_x.ensure(in_e * 4));
+  __nv_bfloat16* xh = e->bw_x.as<__nv_bfloat16>();
+  IBL_RET(launch_f32_to_planes(x, in_e, xh, xh + in_e, s));
+  const int splits = wgrad_tc_splits(N, H, W, L.cin, L.cout);
+  IBL_RET(e->bw_part.ensure(((size_t)splits * 9 * L.cout * L.cin + (size_t)256 * L.cout) * sizeof(float)));
+  float* part = e->bw_part.as<float>();
+  IBL_RET(launch_conv_wgrad_tc(gh, gh + out_e, xh, xh + in_e, N, H, W, L.cin, L.cout, part, splits,
+                               part + (size_t)splits * 9 * L.cout * L.cin, gw, gb, s));
+  e->launches += 5;
+  if (gx) {
+    // dgrad = the forward implicit-GEMM kernel on dY with the 180-degree-rotated, role-swapped filter bank
+    const size_t nw = (size_t)L.cout * L.cin * 9;
+    IBL_RET(e->bw_w.ensure(nw * 4 + (size_t)L.cin * sizeof(float)));
+    ConvParams p;
+    p.w_hi = e->bw_w.as<__nv_bfloat16>();
+    p.w_lo = p.w_hi + nw;
+    p.bias = reinterpret_cast<float*>(p.w_lo + nw);
+    p.cin_pad = L.cout;
+    IBL_CUDA_OK(cudaMemsetAsync(p.bias, 0, (size_t)L.cin * sizeof(float), s));
+    IBL_RET(launch_repack_weights_dgrad(e->conv[layer].w_tck, L.cout, L.cin, p.w_hi, p.w_lo, s));
+    IBL_RET(launch_conv3x3_tc(gh, gh + out_e, p, N, H, W, L.cout, L.cin, false, false, nullptr, nullptr, gx, s));
+    e->launches += 2;
+  }
+  return IBL_OK;
+}
+
 int ibl_netvlad_forward(ibl_engine* e, const float* feat, int nhwc, int N, int C, int S_, const float* conv_w,
                         const float* centroids, int K, int normalize_input, float* vlad_raw,
                         float* vlad_norm, void* stream) {
@@ -372,11 +497,12 @@ int ibl_netvlad_forward(ibl_engine* e, const float* feat, int nhwc, int N, int C
     IBL_RET(launch_row_sqnorm(feat, N * S_, C, e->ssq.as<float>(), s));
     const int G = netvlad_tc_units(N, S_);
     IBL_RET(e->nv_part.ensure((size_t)N * G * 64 * 512 * sizeof(float)));
-    IBL_RET(e->nv_asum.ensure((size_t)N * (netvlad_tc_asum_parts(G) + 1) * 64 * sizeof(float)));
+    IBL_RET(e->nv_asum.ensure((size_t)N * G * 64 * sizeof(float)));
+    IBL_RET(ensure_tickets(e, N, s));
     IBL_RET(launch_netvlad_tc(xh, xh + ne, N, S_, wh, wh + nw, e->ssq.as<float>(), 1, centroids,
-                              normalize_input != 0, e->nv_part.as<float>(), e->nv_asum.as<float>(), vlad_raw,
-                              vlad_norm, s));
-    e->launches += 5;
+                              normalize_input != 0, e->nv_part.as<float>(), e->nv_asum.as<float>(),
+                              e->nv_ticket.as<int>(), vlad_raw, vlad_norm, s));
+    e->launches += 4;
     return IBL_OK;
   }
   IBL_RET(e->nv_assign.ensure((size_t)N * S_ * K * sizeof(float)));
@@ -497,12 +623,13 @@ int ibl_extract(ibl_engine* e, const float* x, int N, int H, int W, unsigned fla
       }
       const int G = netvlad_tc_units(nb, Sp);
       IBL_RET(e->nv_part.ensure((size_t)nb * G * 64 * 512 * sizeof(float)));
-      IBL_RET(e->nv_asum.ensure((size_t)nb * (netvlad_tc_asum_parts(G) + 1) * 64 * sizeof(float)));
+      IBL_RET(e->nv_asum.ensure((size_t)nb * G * 64 * sizeof(float)));
+      IBL_RET(ensure_tickets(e, nb, S(stream)));
       const size_t nw = (size_t)64 * 512;
       IBL_RET(launch_netvlad_tc(fp.hi, fp.lo, nb, Sp, e->nvw_pl.as<__nv_bfloat16>(), e->nvw_pl.as<__nv_bfloat16>() + nw,
                                 e->ssq.as<float>(), fp.ssq_parts, e->nv_c, true, e->nv_part.as<float>(),
-                                e->nv_asum.as<float>(), nullptr, vdst, S(stream)));
-      e->launches += 2;
+                                e->nv_asum.as<float>(), e->nv_ticket.as<int>(), nullptr, vdst, S(stream)));
+      e->launches += 1;                     // ONE launch: partials, centroid term, intra-norm and L2 inside the kernel
     } else {
       IBL_RET(e->feat.ensure((size_t)nb * Sp * 512 * sizeof(float)));
       IBL_RET(vgg_forward_impl(e, xb, nb, H, W, e->feat.as<float>(), S(stream)));
@@ -645,6 +772,40 @@ int ibl_l2dist_dense(ibl_engine* e, const float* q, int m, const float* db, int 
   return IBL_OK;
 }
 
+// C[m,n] = alpha * A[m,k] . B[n,k]^T on the engine's own GEMM kernels (PCA.train's covariance / dual products and
+// projection, reference ibl/pca.py:38-67, torch.matmul there).  mode: IBL_CONV_SIMT_FP32 = fp32 CUDA cores,
+// IBL_CONV_TC_BF16X3 = tcgen05 bf16x3 (k % 64 == 0).  Built on the distance tile with zero norm terms:
+// (0 + 0 - 2 a.b) * (-alpha / 2).
+int ibl_gemm_nt(ibl_engine* e, const float* A, int m, const float* B, int n, int k, float alpha, float* C, int mode,
+                void* stream) {
+  IBL_REQUIRE(e && A && B && C, "null argument");
+  IBL_REQUIRE(m >= 1 && n >= 1 && k >= 4 && k % 4 == 0, "bad shape (k must be a positive multiple of 4)");
+  IBL_REQUIRE((long long)m * n < (1ll << 31), "output too large for one call");
+  IBL_REQUIRE(mode == IBL_CONV_SIMT_FP32 || mode == IBL_CONV_TC_BF16X3, "unknown gemm mode");
+  DeviceGuard g(e->device);
+  cudaStream_t s = S(stream);
+  IBL_RET(e->qn.ensure((size_t)m * sizeof(float)));
+  IBL_RET(e->dbn.ensure((size_t)n * sizeof(float)));
+  IBL_CUDA_OK(cudaMemsetAsync(e->qn.p, 0, (size_t)m * sizeof(float), s));
+  IBL_CUDA_OK(cudaMemsetAsync(e->dbn.p, 0, (size_t)n * sizeof(float), s));
+  if (mode == IBL_CONV_TC_BF16X3 && k % 64 == 0) {
+    const size_t ae = (size_t)m * k, be = (size_t)n * k;
+    IBL_RET(e->q_pl.ensure(ae * 4));
+    IBL_RET(e->db_pl.ensure(be * 4));
+    __nv_bfloat16 *ah = e->q_pl.as<__nv_bfloat16>(), *bh = e->db_pl.as<__nv_bfloat16>();
+    IBL_RET(launch_f32_to_planes(A, ae, ah, ah + ae, s));
+    IBL_RET(launch_f32_to_planes(B, be, bh, bh + be, s));
+    IBL_RET(launch_dist_dense_tc(ah, ah + ae, e->qn.as<float>(), m, bh, bh + be, e->dbn.as<float>(), n, k, C, n, s));
+    e->launches += 3;
+  } else {
+    IBL_RET(launch_l2dist_dense(A, e->qn.as<float>(), m, B, e->dbn.as<float>(), n, k, C, n, s));
+    e->launches += 1;
+  }
+  IBL_RET(launch_scale(C, -0.5f * alpha, m * n, C, s));
+  e->launches += 1;
+  return IBL_OK;
+}
+
 // pairwise_distance(features) with query=gallery=None (evaluators.py:106-114):
 // out[i,j] = 2|x_i|^2 - 2 x_i.x_j  (the reference broadcasts 2|x_i|^2 over the whole row)
 int ibl_l2dist_self(ibl_engine* e, const float* x, int n, int d, float* out, void* stream) {
@@ -678,6 +839,16 @@ int ibl_l2dist_topk(ibl_engine* e, const float* q, int m, const float* db, int n
   IBL_REQUIRE(n_valid >= 0 && n_valid <= n, "n_valid out of range");
   IBL_REQUIRE(k >= 1 && k <= 128, "top-k supports 1 <= k <= 128");
   DeviceGuard g(e->device);
+  // IBL_DIST_SCREEN=3 selects round 1's bf16x3 screening kernels (A/B measurements, variant tests)
+  static const int screen_env = [] { const char* v = getenv("IBL_DIST_SCREEN"); return v ? atoi(v) : 1; }();
+  if (e->gemm_mode == IBL_CONV_TC_BF16X3 && d % 64 == 0 && n_valid > 0 && k <= 12 && m > 128 && screen_env != 3) {
+    // single fp16 tensor-core pass to screen, exact fp32 to decide, guard + exact fallback on the device
+    size_t off[9];
+    IBL_RET(e->d1_ws.ensure(dist1_workspace_bytes(m, n, d, off)));
+    e->d1_m = m; e->d1_n = n; e->d1_d = d;
+    return launch_dist_topk_1pass(q, m, db, n, n_valid, d, k, (long long)idx_base, e->d1_ws.p, out_dist,
+                                  reinterpret_cast<long long*>(out_idx), &e->launches, S(stream));
+  }
   if (e->gemm_mode == IBL_CONV_TC_BF16X3 && d % 64 == 0 && n_valid > 0) {
     cudaStream_t s = S(stream);
     IBL_RET(e->qn.ensure((size_t)m * sizeof(float)));
@@ -826,6 +997,16 @@ int ibl_l2dist_topk_host(ibl_engine* e, const float* q_host, int m, const float*
   IBL_CUDA_OK(cudaMemcpyAsync(out_idx_host, e->stage_out2.p, (size_t)m * k * sizeof(int64_t), cudaMemcpyDeviceToHost, S(stream)));
   IBL_CUDA_OK(cudaStreamSynchronize(S(stream)));
   return IBL_OK;
+}
+
+// test hook: how many queries the guard of the single-pass distance path listed in the last ibl_l2dist_topk call
+// (they were re-ranked by exact brute force on the device).  Synchronises the stream.
+int ibl_debug_dist_flagged(ibl_engine* e, int* count, void* stream) {
+  IBL_REQUIRE(e && count, "null argument");
+  *count = -1;
+  if (!e->d1_ws.p || !e->d1_m) return IBL_OK;
+  DeviceGuard g(e->device);
+  return dist1_last_flag_count(e->d1_ws.p, e->d1_m, e->d1_n, e->d1_d, count, S(stream));
 }
 
 int ibl_selftest_tc(ibl_engine* e, float* max_rel_err) {

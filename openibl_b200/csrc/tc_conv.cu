@@ -583,8 +583,11 @@ int launch_conv3x3_tc(const __nv_bfloat16* x_hi, const __nv_bfloat16* x_lo, cons
   // N tile: 256 where Cout allows and there are enough patches to fill the machine (measured
   // 5-9 % faster than 128 on conv3_x/conv4_x: 96 vs 128 B/clk of shared-memory operand reads per
   // MMA); 128 otherwise; 64 only for Cout = 64 (profiles/r01_bench_layers_v1.txt).
+  // The choice depends on the IMAGE geometry only (a nominal batch of 32), never on the actual batch: the variants
+  // walk K in different orders (halo: chunk-major, im2col boxes: tap-major), so a batch-dependent choice would make
+  // an image's descriptor depend on the batch it travels in (tests: bit-identical across batch compositions).
   int bn = cout % 128 == 0 ? 128 : 64;
-  if (cout % 256 == 0 && (long long)N * a.tiles_h * a.tiles_w * (cout / 256) >= 4 * 148) bn = 256;
+  if (cout % 256 == 0 && 32ll * a.tiles_h * a.tiles_w * (cout / 256) >= 4 * 148) bn = 256;
   if (g_tc_bn_override && cout % g_tc_bn_override == 0) bn = g_tc_bn_override;
   {
     static int env_bn = -1;   // experiment hook: IBL_TC_BN=256 forces the N tile where it divides Cout

@@ -137,9 +137,12 @@ int debug_gemm_tn(const float* A, const float* B, float* C, cudaStream_t s) {
 //   vlad[k,c] = V[c,k] - cent[k,c] * sum_s a[s,k]
 //
 // One work unit = (image, every G-th 128-pixel tile); a unit keeps V (512 x 64 fp32 = 256 TMEM columns)
-// resident across its tiles and writes one partial; `netvlad_finalize_kernel` adds the G partials,
-// subtracts the centroid term and applies the two normalisations.  The feature map is read from HBM
-// once (the second pass over a tile's channel chunks hits L2).  Both contractions are bf16x3.
+// resident across its tiles and writes one partial.  ONE LAUNCH: the unit that arrives last for an image
+// (atomic ticket in global memory) adds the G partials in index order (L2 hits), subtracts the centroid term
+// and applies the intra-normalisation and the global L2 (netvlad.py:78-80) before the kernel ends -- there is
+// no finalize kernel.  G depends on S only, never on the batch, so an image's descriptor is bit-identical
+// whatever batch it travels in.  The feature map is read from HBM once (the second pass over a tile's
+// channel chunks hits L2).  Both contractions are bf16x3.
 // The logits are double buffered in TMEM (128 + 128 columns) and GEMM 1 of the next tile is issued before
 // GEMM 2 of the current one, so the softmax runs under tensor-core work (44 -> 35 us at B = 32).
 //
@@ -154,6 +157,10 @@ struct NvTcArgs {
   int normalize_input;
   float* part;                    // [B*G][64][512]   partial V^T (k-major rows, c contiguous)
   float* asum_part;               // [B*G][64]
+  const float* cent;              // [64][512] centroids
+  float* vlad_raw;                // [B][64][512] un-normalised VLAD (nullable)
+  float* vlad_norm;               // [B][64*512] intra-normalised + L2-normalised descriptor (nullable)
+  int* ticket;                    // [B] zero on entry; the unit that takes ticket G-1 finalises the image and resets it
   unsigned long long* dbg;        // optional [gridDim][32] globaltimer stamps (IBL_NV_DEBUG=1)
 };
 
@@ -184,6 +191,78 @@ struct NvIter {
     if (t >= T) { u += stride; ++useq; t = u % G; }
   }
 };
+
+// Finalisation of image b by the four epilogue warps (128 threads) of the unit that arrived last:
+//   vlad[k,c] = sum_g part[b,g,k,c] - cent[k,c] * sum_g asum[b,g,k]   (partials added in index order: deterministic)
+//   intra-normalise every cluster row (netvlad.py:78), flatten k-major, global L2 (:79-80).
+// Warp q owns rows q*16 .. q*16+15, lane L the channels L, L+32, ...; every thread rescales exactly the elements it
+// wrote itself, so the second pass needs no fence.  `sm` is the 260-float asum scratch of the kernel.
+__device__ __forceinline__ void nv_finalize_image(const NvTcArgs& a, int b, int q, int lane, float* sm) {
+  const int tid = q * 32 + lane;
+  const long long ub = (long long)b * a.G;
+  if (tid < 64) {
+    float s = 0.f;
+    for (int g = 0; g < a.G; ++g) s += __ldcg(a.asum_part + (ub + g) * 64 + tid);
+    sm[tid] = s;
+  }
+  asm volatile("bar.sync 1, 128;" ::: "memory");
+  float tot = 0.f;
+  // Latency-bound on one SM (640 KB from L2): every row iteration issues its 16 x G loads before the first add.
+#pragma unroll 1
+  for (int r = 0; r < 16; ++r) {
+    const int k = q * 16 + r;
+    const float asum = sm[k];
+    float v[16], cz[16];
+#pragma unroll
+    for (int j = 0; j < 16; ++j) { v[j] = 0.f; cz[j] = __ldg(a.cent + k * 512 + lane + 32 * j); }
+#pragma unroll
+    for (int g = 0; g < 4; ++g) {                      // G <= 4 (netvlad_tc_units); partials added in index order
+      if (g < a.G) {
+        const float* pg = a.part + ((ub + g) * 64 + k) * 512 + lane;
+        float t[16];
+#pragma unroll
+        for (int j = 0; j < 16; ++j) t[j] = __ldcg(pg + 32 * j);
+#pragma unroll
+        for (int j = 0; j < 16; ++j) v[j] += t[j];
+      }
+    }
+    float ss = 0.f;
+#pragma unroll
+    for (int j = 0; j < 16; ++j) {
+      v[j] -= cz[j] * asum;
+      ss = fmaf(v[j], v[j], ss);
+    }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) ss += __shfl_xor_sync(0xffffffffu, ss, o);
+    const float inv = 1.f / fmaxf(sqrtf(ss), 1e-12f);
+    float s2 = 0.f;
+    const long long row = ((long long)b * 64 + k) * 512;
+#pragma unroll
+    for (int j = 0; j < 16; ++j) {
+      const int c = lane + 32 * j;
+      if (a.vlad_raw) a.vlad_raw[row + c] = v[j];
+      const float w = v[j] * inv;
+      s2 = fmaf(w, w, s2);
+      if (a.vlad_norm) a.vlad_norm[row + c] = w;
+    }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) s2 += __shfl_xor_sync(0xffffffffu, s2, o);
+    tot += s2;
+  }
+  if (!a.vlad_norm) return;                          // block-uniform
+  if (lane == 0) sm[128 + q] = tot;
+  asm volatile("bar.sync 1, 128;" ::: "memory");
+  const float ginv = 1.f / fmaxf(sqrtf((sm[128] + sm[129]) + (sm[130] + sm[131])), 1e-12f);
+#pragma unroll 1
+  for (int r4 = 0; r4 < 4; ++r4) {                   // 4 rows = 64 independent loads per thread in flight
+    float* o = a.vlad_norm + ((long long)b * 64 + q * 16 + r4 * 4) * 512 + lane;
+    float t[64];
+#pragma unroll
+    for (int i = 0; i < 64; ++i) t[i] = o[(i >> 4) * 512 + 32 * (i & 15)];
+#pragma unroll
+    for (int i = 0; i < 64; ++i) o[(i >> 4) * 512 + 32 * (i & 15)] = t[i] * ginv;
+  }
+}
 
 // Software pipeline over the CTA's tile list: GEMM 1 of tile i+1 is issued BEFORE GEMM 2 of tile i, so the
 // tensor core computes the next logits while the epilogue warps run the softmax of tile i (logits are double
@@ -490,13 +569,29 @@ netvlad_tc_kernel(const __grid_constant__ CUtensorMap tm_xhi, const __grid_const
         tc_fence_before();
         // the four epilogue warps meet (named barrier 1) before their asum partials are combined
         asm volatile("bar.sync 1, 128;" ::: "memory");
+        if (lane == 0) mbar_arrive(d_empty);         // V has been read out of TMEM: the next unit's GEMM 2 may start
         if (threadIdx.x - 64 < 64) {
           const int k = threadIdx.x - 64;
           a.asum_part[(long long)unit * 64 + k] = asum_sm[k] + asum_sm[64 + k] + asum_sm[128 + k] + asum_sm[192 + k];
         }
+        // ---- last unit of the image finalises it (threadfence-reduction pattern) ----
+        __threadfence();                             // this thread's partial is visible device-wide
         asm volatile("bar.sync 1, 128;" ::: "memory");
-        if (lane == 0) mbar_arrive(d_empty);
+        int* flag_sm = reinterpret_cast<int*>(asum_sm + 256);
+        if (threadIdx.x == 64) {
+          const int tk = atomicAdd(a.ticket + b, 1);
+          const int lastu = (tk == a.G - 1) ? 1 : 0;
+          if (lastu) a.ticket[b] = 0;                // self-cleaning: the next launch finds zeros again
+          *flag_sm = lastu;
+        }
+        asm volatile("bar.sync 1, 128;" ::: "memory");
         NV_STAMP(dslot); ++dslot;                    // partial written
+        if (*flag_sm) {
+          __threadfence();
+          nv_finalize_image(a, b, q, lane, asum_sm);
+          NV_STAMP(dslot); ++dslot;                  // image finalised
+        }
+        asm volatile("bar.sync 1, 128;" ::: "memory");   // flag_sm / asum_sm are reused by the next unit
         as0 = 0.f; as1 = 0.f;
         dslot = 1;
       }
@@ -507,84 +602,22 @@ netvlad_tc_kernel(const __grid_constant__ CUtensorMap tm_xhi, const __grid_const
   if (warp == 1) { tc_fence_after(); tmem_dealloc(tmem_base, 512); }
 }
 
-// vlad[k,c] = sum_g part[b,g,k,c] - cent[k,c] * sum_g asum[b,g,k]; intra-normalise (netvlad.py:78).
-// grid (8, B): one warp per cluster row, 16 channels per lane held in registers.  Writes the raw VLAD
-// (if asked), the intra-normalised rows, and each row's squared norm for the global L2 pass.
-__global__ void __launch_bounds__(256)
-netvlad_finalize_rows_kernel(const float* __restrict__ part, const float* __restrict__ asum_part, int G, int AG,
-                             const float* __restrict__ cent, float* __restrict__ vlad_raw /*nullable*/,
-                             float* __restrict__ vlad_norm /*nullable*/, float* __restrict__ row_ss /*[B][64]*/) {
-  const long long b = blockIdx.y;
-  const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
-  const int k = blockIdx.x * 8 + wid;
-  float asum = 0.f;
-  for (int g = 0; g < AG; ++g) asum += __ldg(asum_part + (b * AG + g) * 64 + k);   // AG partials of sum_s a
-  float v[16];
-  float ss = 0.f;
-#pragma unroll
-  for (int j = 0; j < 16; ++j) {
-    const int c = lane + 32 * j;
-    float acc = 0.f;
-    for (int g = 0; g < G; ++g) acc += __ldg(part + ((b * G + g) * 64 + k) * 512 + c);
-    acc -= __ldg(cent + k * 512 + c) * asum;
-    v[j] = acc;
-    ss = fmaf(acc, acc, ss);
-  }
-#pragma unroll
-  for (int o = 16; o > 0; o >>= 1) ss += __shfl_xor_sync(0xffffffffu, ss, o);
-  const float inv = 1.f / fmaxf(sqrtf(ss), 1e-12f);
-  float s2 = 0.f;
-#pragma unroll
-  for (int j = 0; j < 16; ++j) {
-    const int c = lane + 32 * j;
-    if (vlad_raw) vlad_raw[(b * 64 + k) * 512 + c] = v[j];
-    const float w = v[j] * inv;
-    s2 = fmaf(w, w, s2);
-    if (vlad_norm) vlad_norm[(b * 64 + k) * 512 + c] = w;
-  }
-#pragma unroll
-  for (int o = 16; o > 0; o >>= 1) s2 += __shfl_xor_sync(0xffffffffu, s2, o);
-  if (lane == 0) row_ss[b * 64 + k] = s2;
-}
-
-// global L2 over the flattened 64x512 descriptor (netvlad.py:79-80): grid (8, B), in place
-__global__ void __launch_bounds__(256)
-netvlad_finalize_l2_kernel(float* __restrict__ vlad_norm, const float* __restrict__ row_ss) {
-  const long long b = blockIdx.y;
-  const int lane = threadIdx.x & 31;
-  float tot = __ldg(row_ss + b * 64 + lane) + __ldg(row_ss + b * 64 + lane + 32);
-#pragma unroll
-  for (int o = 16; o > 0; o >>= 1) tot += __shfl_xor_sync(0xffffffffu, tot, o);
-  const float ginv = 1.f / fmaxf(sqrtf(tot), 1e-12f);
-  float4* o = reinterpret_cast<float4*>(vlad_norm + (b * 64 + blockIdx.x * 8) * 512);
-  for (int e = threadIdx.x; e < 8 * 512 / 4; e += 256) {
-    float4 w = o[e];
-    w.x *= ginv; w.y *= ginv; w.z *= ginv; w.w *= ginv;
-    o[e] = w;
-  }
-}
-
 // (A 4-CTA-cluster variant that reads every feature byte once -- channels split over the cluster, partial logits
 // reduce-scattered and a' all-gathered through DSMEM -- was parity-green but measured 62-77 us against 35 us for
 // this kernel and was removed from the product library; see git history, round 1: tc_netvlad4.cu.)
-int netvlad_tc_asum_parts(int G) { return G; }
-
+// Units per image: a function of S ONLY (never of the batch), so that an image's partial sums are formed and added
+// in the same order whatever batch it is part of -- descriptors are bit-identical across batch compositions and world
+// sizes (the 250k gallery ranks identically on 1 and 8 GPUs).  4 units x 32 images = 128 CTAs for the batch-32 step.
 int netvlad_tc_units(int B, int S) {
-  int sms = 148;
-  int dev = 0;
-  cudaGetDevice(&dev);
-  cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+  (void)B;
   const int T = cdiv(S, 128);
-  int G = sms / (B > 0 ? B : 1);
-  if (G < 1) G = 1;
-  if (G > T) G = T;
-  return G;
+  return T < 4 ? T : 4;
 }
 
 // x planes [B,S,512] (hi, lo), w planes [64,512] (hi, lo), ssq [parts][B*S], cent [64,512] fp32
 int launch_netvlad_tc(const __nv_bfloat16* x_hi, const __nv_bfloat16* x_lo, int B, int S,
                       const __nv_bfloat16* w_hi, const __nv_bfloat16* w_lo, const float* ssq, int ssq_parts,
-                      const float* cent, bool normalize_input, float* part, float* asum_part,
+                      const float* cent, bool normalize_input, float* part, float* asum_part, int* ticket,
                       float* vlad_raw, float* vlad_norm, cudaStream_t s) {
   CUtensorMap mx_hi, mx_lo, mw_hi, mw_lo;
   {
@@ -605,13 +638,14 @@ int launch_netvlad_tc(const __nv_bfloat16* x_hi, const __nv_bfloat16* x_lo, int 
   a.B = B; a.S = S; a.T = cdiv(S, 128); a.G = netvlad_tc_units(B, S);
   a.ssq = ssq; a.ssq_parts = ssq_parts; a.normalize_input = normalize_input ? 1 : 0;
   a.part = part; a.asum_part = asum_part;
+  a.cent = cent; a.vlad_raw = vlad_raw; a.vlad_norm = vlad_norm; a.ticket = ticket;
   static unsigned long long* dbg_dev = nullptr;
   static int dbg_on = -1;
   if (dbg_on < 0) { const char* v = getenv("IBL_NV_DEBUG"); dbg_on = (v && atoi(v)) ? 1 : 0; }
   if (dbg_on && !dbg_dev) { cudaMalloc(&dbg_dev, 148 * 32 * 8); }
   if (dbg_on) cudaMemsetAsync(dbg_dev, 0, 148 * 32 * 8, s);
   a.dbg = dbg_on ? dbg_dev : nullptr;
-  const int smem = NV_NSTAGE * NV_STAGE + 2 * NV_SLOT + 1024 + 128 + 4 * 64 * 4;
+  const int smem = NV_NSTAGE * NV_STAGE + 2 * NV_SLOT + 1024 + 128 + 4 * 64 * 4 + 16;
   static DeviceOnce attr_done;   // the attribute is per device
   if (!attr_done.done()) {
     IBL_CUDA_OK(cudaFuncSetAttribute(netvlad_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
@@ -621,7 +655,6 @@ int launch_netvlad_tc(const __nv_bfloat16* x_hi, const __nv_bfloat16* x_lo, int 
   cudaGetDevice(&dev);
   cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
   const int units = B * a.G;
-  const int AG = netvlad_tc_asum_parts(a.G);
   netvlad_tc_kernel<<<units < sms ? units : sms, 192, smem, s>>>(mx_hi, mx_lo, mw_hi, mw_lo, a);
   IBL_CUDA_OK(cudaGetLastError());
   if (dbg_on) {   // print phase stamps of a few CTAs (ns relative to the earliest stamp)
@@ -635,13 +668,6 @@ int launch_netvlad_tc(const __nv_bfloat16* x_hi, const __nv_bfloat16* x_lo, int 
       for (int j = 0; j < 12; ++j) fprintf(stderr, " %6lld", h[c * 32 + j] ? (long long)(h[c * 32 + j] - t0) : -1ll);
       fprintf(stderr, "\n");
     }
-  }
-  float* row_ss = asum_part + (size_t)B * AG * 64;   // caller sizes asum_part as [B * (AG + 1)][64]
-  netvlad_finalize_rows_kernel<<<dim3(8, B), 256, 0, s>>>(part, asum_part, a.G, AG, cent, vlad_raw, vlad_norm, row_ss);
-  IBL_CUDA_OK(cudaGetLastError());
-  if (vlad_norm) {
-    netvlad_finalize_l2_kernel<<<dim3(8, B), 256, 0, s>>>(vlad_norm, row_ss);
-    IBL_CUDA_OK(cudaGetLastError());
   }
   return IBL_OK;
 }

@@ -342,6 +342,91 @@ class Engine:
               "ibl_l2dist_topk_host")
         return out_dist_host, out_idx_host
 
+    def dist_flagged(self) -> int:
+        """Queries re-ranked by exact brute force in the last l2dist_topk call (-1: single-pass path not taken)."""
+        c = c_int()
+        check(self.lib.ibl_debug_dist_flagged(self.h, byref(c), _stream(self.device)), "ibl_debug_dist_flagged")
+        return c.value
+
+    def gemm_nt(self, a: torch.Tensor, b: torch.Tensor, alpha: float = 1.0, mode: int = CONV_SIMT_FP32) -> torch.Tensor:
+        """alpha * a @ b.T on the engine's own GEMM kernels (PCA.train's products, pca.py:38-67)."""
+        a = _require_cuda(a, "A")
+        b = _require_cuda(b, "B")
+        m, k = a.shape
+        n = b.shape[0]
+        if b.shape[1] != k:
+            raise ValueError("gemm_nt: inner dimensions differ")
+        pad = (-k) % 64
+        if pad:                                   # zero columns do not change the products
+            a = torch.nn.functional.pad(a, (0, pad))
+            b = torch.nn.functional.pad(b, (0, pad))
+        out = torch.empty(m, n, device=a.device)
+        rows = max(1, min(m, (2 ** 31 - 1) // max(n, 1)))
+        for r0 in range(0, m, rows):
+            r1 = min(m, r0 + rows)
+            check(self.lib.ibl_gemm_nt(self.h, _ptr(a[r0:r1]), r1 - r0, _ptr(b), n, k + pad, c_float(alpha), _ptr(out[r0:r1]),
+                                       int(mode), _stream(self.device)), "ibl_gemm_nt")
+        return out
+
+    # ---- training surface of the trunk (SURVEY 8 f1) ------------------------------------------
+    def vgg16_prefix_forward(self, x: torch.Tensor, n_layers: int) -> torch.Tensor:
+        """Frozen layers [0, n_layers) -> fp32 NHWC activation entering layer n_layers."""
+        from .synth import VGG16_PLAN
+        x = _require_cuda(x, "input images")
+        N, _, H, W = x.shape
+        h, w, c, seen = H, W, 3, 0
+        for item in VGG16_PLAN:
+            if item == "P":
+                h, w = h // 2, w // 2
+            else:
+                if seen == n_layers:
+                    break
+                c = item[2]
+                seen += 1
+        out = torch.empty(N, h, w, c, device=x.device)
+        check(self.lib.ibl_vgg16_prefix_forward(self.h, _ptr(x), N, H, W, int(n_layers), _ptr(out), _stream(self.device)),
+              "ibl_vgg16_prefix_forward")
+        return out
+
+    def vgg16_layer_forward(self, layer: int, x: torch.Tensor, cout: int) -> torch.Tensor:
+        x = _require_cuda(x, "layer input")
+        if layer == 0:
+            N, _, H, W = x.shape
+        else:
+            N, H, W, _ = x.shape
+        y = torch.empty(N, H, W, cout, device=x.device)
+        check(self.lib.ibl_vgg16_layer_forward(self.h, int(layer), _ptr(x), N, H, W, _ptr(y), _stream(self.device)),
+              "ibl_vgg16_layer_forward")
+        return y
+
+    def vgg16_layer_backward(self, layer: int, x: torch.Tensor, y: Optional[torch.Tensor], gy: torch.Tensor,
+                             w_shape, need_gx: bool):
+        x = _require_cuda(x, "layer input")
+        gy = _require_cuda(gy, "grad output")
+        N, H, W, cout = gy.shape
+        gx = torch.empty_like(x) if need_gx else None
+        gw = torch.empty(w_shape, device=x.device)
+        gb = torch.empty(cout, device=x.device)
+        check(self.lib.ibl_vgg16_layer_backward(self.h, int(layer), _ptr(x), _ptr(y), _ptr(gy), N, H, W, _ptr(gx), _ptr(gw),
+                                                _ptr(gb), _stream(self.device)), "ibl_vgg16_layer_backward")
+        return gx, gw, gb
+
+    def maxpool2x2(self, x: torch.Tensor) -> torch.Tensor:
+        x = _require_cuda(x, "pool input")
+        N, H, W, C = x.shape
+        y = torch.empty(N, H // 2, W // 2, C, device=x.device)
+        check(self.lib.ibl_maxpool2x2_forward(self.h, _ptr(x), N, H, W, C, _ptr(y), _stream(self.device)), "ibl_maxpool2x2_forward")
+        return y
+
+    def maxpool2x2_backward(self, x: torch.Tensor, gy: torch.Tensor) -> torch.Tensor:
+        x = _require_cuda(x, "pool input")
+        gy = _require_cuda(gy, "pool grad")
+        N, H, W, C = x.shape
+        gx = torch.empty_like(x)
+        check(self.lib.ibl_maxpool2x2_backward(self.h, _ptr(x), _ptr(gy), N, H, W, C, _ptr(gx), _stream(self.device)),
+              "ibl_maxpool2x2_backward")
+        return gx
+
     # ---- test hooks ----------------------------------------------------------------------
     def debug_conv3x3(self, x_nhwc, w_oihw, bias, relu=True, pool=False, mode=CONV_TC_BF16X3, bn=0):
         x = _require_cuda(x_nhwc, "x")

@@ -4,7 +4,8 @@ Shared by bench.py (`strong_250k`), tools/bench_gallery.py and tests/test_gpu_e2
 
 Every image is generated on the device from a seed that depends only on its GLOBAL index, so the gallery --
 and therefore every descriptor, every distance and the final ranking -- is the same whatever the world
-size.  Query j is a noisy copy of database image pos[j] (so Recall@N is a real, non-trivial number).
+size.  Query j is a noisy copy of database image pos[j] (so Recall@N is a real, non-trivial number); images are smooth
+random fields, not white noise, so that descriptors of different images are 2e-2..7e-2 apart.
 
 Flow (reference: ibl/evaluators.py:76-101,105-130,142-167 is what it replaces):
   1. rank r extracts its DistributedSliceSampler slice of the database and of the queries
@@ -26,7 +27,7 @@ from .evaluators import recalls_from_topk, sharded_topk, _all_gather_rows
 from .utils.data.sampler import slice_bounds
 
 SEED_DB, SEED_Q, SEED_POS = 1_000_003, 7_000_003, 12345
-NOISE = 0.35
+NOISE, AMP = 0.5, 2.0
 
 
 def planted_positives(n_db: int, n_q: int) -> np.ndarray:
@@ -34,14 +35,21 @@ def planted_positives(n_db: int, n_q: int) -> np.ndarray:
 
 
 def make_image_batch(kind: str, first: int, count: int, H: int, W: int, dev, pos=None, out=None) -> torch.Tensor:
-    """Images [count,3,H,W] with global indices first..first+count-1; `kind` is 'db' or 'q'."""
+    """Images [count,3,H,W] with global indices first..first+count-1; `kind` is 'db' or 'q'.
+
+    A database image is a smooth random field (a 3 x H/16 x W/16 normal sample, seeded by the image's global index,
+    bilinearly upsampled and scaled by 2): white noise would give every image almost the same descriptor through a
+    random-init trunk (all pairwise distances ~1e-6), smooth structure gives distances of 2e-2..7e-2.  Query j is the
+    field of database image pos[j] plus 0.5-sigma white noise seeded by j."""
     x = out if out is not None else torch.empty(count, 3, H, W, device=dev)
     g = torch.Generator(device=dev)
+    ch, cw = max(H // 16, 2), max(W // 16, 2)
     for j in range(count):
         i = first + j
         base = i if kind == "db" else int(pos[i])
         g.manual_seed(SEED_DB + base)
-        x[j].normal_(generator=g)
+        coarse = torch.randn(1, 3, ch, cw, device=dev, generator=g)
+        x[j] = torch.nn.functional.interpolate(coarse, size=(H, W), mode="bilinear", align_corners=False)[0] * AMP
         if kind == "q":
             g.manual_seed(SEED_Q + i)
             x[j].add_(torch.randn(3, H, W, device=dev, generator=g), alpha=NOISE)

@@ -6,8 +6,10 @@ torch ops: it hands raw device pointers to libiblb200.so.  Parameters stay ordin
 `nn.Parameter`s (DDP wrapping, `.cuda()`, `load_state_dict`, `copy_state_dict` all work);
 the engine re-lays them out when their version counters change.
 
-No CPU path: calling a model on CPU tensors raises.  Training (autograd through NetVLAD,
-EmbedRegionNet's train branch, netvlad.py:123-207) is listed as "next" in SURVEY 8(f).
+No CPU path: calling a model on CPU tensors raises.  Training (config 5): NetVLAD and the trainable
+suffix of the VGG trunk (conv5_x when `train_layers='conv5'`, vgg.py:50-53) are `torch.autograd.Function`s whose
+forward AND backward run in libiblb200 (tcgen05 dgrad / wgrad, NetVLAD backward kernels); the region algebra of
+EmbedRegionNet's train branch (sums of quarter VLADs, two normalisations, a 9x9 matmul per pair) stays in torch.
 """
 from __future__ import annotations
 
@@ -18,6 +20,63 @@ from .engine import Engine, invalidate_caches
 from .synth import VGG16_PLAN
 
 __all__ = ["VGG", "vgg16", "NetVLAD", "EmbedNet", "EmbedNetPCA", "EmbedRegionNet", "create", "names"]
+
+
+_POOL_AFTER = [i for i, item in enumerate(VGG16_PLAN) if item == "P"]
+
+
+def _layer_table():
+    """[(cin, cout, relu, pool)] for the 13 conv layers, in order."""
+    convs, pools = [], set()
+    for item in VGG16_PLAN:
+        if item == "P":
+            pools.add(len(convs) - 1)
+        else:
+            convs.append(item)
+    return [(c[1], c[2], i != len(convs) - 1, i in pools) for i, c in enumerate(convs)]
+
+
+class _VGGTrunkFunction(torch.autograd.Function):
+    """VGG.forward with a trainable suffix (layers first..12): frozen prefix on the inference kernels, then one
+    conv(+ReLU) at a time keeping (input, post-ReLU output) for the backward; pools are separate so that the pre-pool
+    activation is available.  Backward: ReLU mask + tcgen05 dgrad/wgrad per layer (ibl_vgg16_layer_backward),
+    first-maximum 2x2 pool backward.  Gradients come back in the parameters' own layouts (OIHW, [Cout])."""
+
+    @staticmethod
+    def forward(ctx, x, first, *params):
+        eng = Engine.get(x.device)
+        table = _layer_table()
+        a = eng.vgg16_prefix_forward(x, first) if first > 0 else x.contiguous()
+        saved = []
+        for l in range(first, 13):
+            cin, cout, relu, pool = table[l]
+            y = eng.vgg16_layer_forward(l, a, cout)
+            saved.append(a)
+            saved.append(y)
+            a = eng.maxpool2x2(y) if pool else y
+        ctx.first = first
+        ctx.w_shapes = [tuple(p.shape) for p in params[0::2]]
+        ctx.save_for_backward(*saved)
+        return a.permute(0, 3, 1, 2).contiguous()            # the reference returns NCHW (vgg.py:70)
+
+    @staticmethod
+    def backward(ctx, grad_nchw):
+        saved = ctx.saved_tensors
+        eng = Engine.get(grad_nchw.device)
+        table = _layer_table()
+        first = ctx.first
+        g = grad_nchw.permute(0, 2, 3, 1).contiguous()
+        grads = [None] * (2 * (13 - first))
+        for l in range(12, first - 1, -1):
+            i = l - first
+            a_in, y = saved[2 * i], saved[2 * i + 1]
+            cin, cout, relu, pool = table[l]
+            if pool:
+                g = eng.maxpool2x2_backward(y, g)
+            gx, gw, gb = eng.vgg16_layer_backward(l, a_in, y if relu else None, g, ctx.w_shapes[i], need_gx=l > first)
+            grads[2 * i], grads[2 * i + 1] = gw, gb
+            g = gx
+        return (None, None, *grads)
 
 
 def _no_train(module: nn.Module, what: str) -> None:
@@ -112,9 +171,25 @@ class VGG(nn.Module):
         eng.set_vgg16(ws, bs, force=self.training and any(w.requires_grad for w in ws))
         return eng
 
+    def first_trainable_layer(self):
+        """Index (0..12) of the first conv layer with a trainable parameter, or 13 if the trunk is frozen."""
+        ws, bs = self.conv_params()
+        for i, (w, b) in enumerate(zip(ws, bs)):
+            if w.requires_grad or b.requires_grad:
+                return i
+        return 13
+
     def forward(self, x):
-        _no_train(self, "VGG.forward")
         eng = self._bind(x)
+        first = self.first_trainable_layer() if (self.training and torch.is_grad_enabled()) else 13
+        if first < 13:
+            # training: the suffix [first, 12] is differentiated (vgg.py:50-53 freezes the prefix for 'conv5' etc.)
+            ws, bs = self.conv_params()
+            flat = [t for l in range(first, 13) for t in (ws[l], bs[l])]
+            feat = _VGGTrunkFunction.apply(x, first, *flat)
+            if self.cut_at_pooling:
+                return feat
+            return torch.nn.functional.adaptive_max_pool2d(feat, 1).view(feat.size(0), -1), feat
         _, feat, pool = eng.vgg16_forward(x, want_nchw=True, want_pool=not self.cut_at_pooling)
         if self.cut_at_pooling:
             return feat
@@ -205,8 +280,16 @@ class _EmbedBase(nn.Module):
 class EmbedNet(_EmbedBase):
     """netvlad.py:63-82: forward -> (pool_x [B,512], vlad_x [B,K*C]) with intra-norm + L2."""
 
+    def _train_forward(self, x):
+        # differentiable path (netvlad_img.py training): trunk suffix + NetVLAD in libiblb200 through their
+        # autograd Functions, the two normalisations (netvlad.py:78-80) as torch ops on [B,64,512]
+        pool_x, feat = self.base_model(x)
+        v = torch.nn.functional.normalize(self.net_vlad(feat), p=2, dim=2)
+        return pool_x, torch.nn.functional.normalize(v.view(x.size(0), -1), p=2, dim=1)
+
     def forward(self, x):
-        _no_train(self, "EmbedNet.forward")
+        if self.training and torch.is_grad_enabled():
+            return self._train_forward(x)
         eng = self._bind(x)
         vlad, pool = eng.extract(x, pca=False, want_pool=True)
         return pool, vlad
@@ -220,7 +303,7 @@ class EmbedNetPCA(_EmbedBase):
         self.pca_layer = nn.Conv2d(net_vlad.num_clusters * net_vlad.dim, dim, 1, stride=1, padding=0)
 
     def forward(self, x):
-        _no_train(self, "EmbedNetPCA.forward")
+        _no_train(self, "EmbedNetPCA.forward")     # the reference never trains the PCA wrapper either (inference only)
         eng = self._bind(x)
         eng.set_pca(self.pca_layer.weight, self.pca_layer.bias)
         out, _ = eng.extract(x, pca=True, want_pool=False)
@@ -230,9 +313,7 @@ class EmbedNetPCA(_EmbedBase):
 class EmbedRegionNet(_EmbedBase):
     """netvlad.py:112-207.  Eval: (pool, vlad) like EmbedNet (:199-205).  Train: the SFRS region branch
     (:123-194) -- quarter / half / global region VLADs of the anchor and of every pair image and their 9x9
-    similarity matrix.  NetVLAD runs (forward and backward) in libiblb200; the VGG trunk is evaluated by the
-    engine without a graph, i.e. it is treated as frozen (conv backward kernels are not built yet), so only
-    `net_vlad.*` receives gradients."""
+    similarity matrix.  NetVLAD and the trainable part of the VGG trunk run forward and backward in libiblb200."""
 
     def __init__(self, base_model, net_vlad, tuple_size=1):
         super().__init__(base_model, net_vlad)
@@ -270,12 +351,11 @@ class EmbedRegionNet(_EmbedBase):
         return score, va, vb
 
     def forward(self, x):
-        eng = self._bind(x)
         if not self.training:
+            eng = self._bind(x)
             vlad, pool = eng.extract(x, pca=False, want_pool=True)
             return pool, vlad
-        with torch.no_grad():
-            _, feat, _ = eng.vgg16_forward(x, want_nchw=True, want_pool=False)
+        _, feat = self.base_model(x)          # differentiable through the trainable suffix of the trunk
         return self._forward_train(feat)
 
 

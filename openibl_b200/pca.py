@@ -50,26 +50,39 @@ class PCA:
 
     # ---- reference API -------------------------------------------------------------------
     def train(self, x):
-        """pca.py:28-84 (relja_PCA): covariance or dual eigen-decomposition.  torch.symeig no longer
-        exists; torch.linalg.eigh has the same ascending-eigenvalue contract.  Runs on the GPU when
-        there is one (cuSOLVER library call -- PCA fitting is SURVEY 8f "next", not the hot path)."""
+        """pca.py:28-84 (relja_PCA): covariance or dual eigen-decomposition of the centred descriptors.
+
+        The matrix products -- the [dims,dims] covariance or the [pts,pts] dual Gram matrix (10k x 10k x 32768 for
+        examples/test.py:108-121), the back-projection U = X V and U^T mu -- run on the engine's own fp32 GEMM kernel
+        (ibl_gemm_nt); the symmetric eigen-decomposition is torch.linalg.eigh (cuSOLVER; torch.symeig, which the
+        reference calls, no longer exists -- same ascending-eigenvalue contract).  GPU only, like the rest of the
+        engine."""
         print("calculating PCA parameters...")
-        dev = torch.device("cuda") if torch.cuda.is_available() else x.device
-        x = x.to(dev).t()
-        n_pts, n_dims = x.size(1), x.size(0)
-        mu = x.mean(1, keepdim=True)
-        x = x - mu
+        if not torch.cuda.is_available():
+            raise RuntimeError("PCA.train runs on the GPU engine (there is no CPU fallback)")
+        from ._cabi import CONV_SIMT_FP32
+        dev = x.device if x.is_cuda else torch.device("cuda", torch.cuda.current_device())
+        eng = Engine.get(dev)
+        rows = x.to(dev).float().contiguous()                 # [pts, dims]: one descriptor per row
+        n_pts, n_dims = rows.shape
+        mu_row = rows.mean(0, keepdim=True)
+        rows = rows - mu_row                                  # centred, still [pts, dims]
         dual = n_dims > n_pts
-        x2 = (x.t() @ x if dual else x @ x.t()) / (n_pts - 1)
+        if dual:
+            x2 = eng.gemm_nt(rows, rows, alpha=1.0 / (n_pts - 1), mode=CONV_SIMT_FP32)            # X^T X, [pts,pts]
+        else:
+            cols = rows.t().contiguous()                                                          # X, [dims,pts]
+            x2 = eng.gemm_nt(cols, cols, alpha=1.0 / (n_pts - 1), mode=CONV_SIMT_FP32)            # X X^T, [dims,dims]
         L, U = torch.linalg.eigh(x2)
         if self.pca_n_components < x2.size(0):
             keep = torch.argsort(L, descending=True)[: self.pca_n_components]
             L, U = L[keep], U[:, keep]
         lams = L.clamp_min(1e-9)
         if dual:
-            U = x @ (U @ torch.diag(1.0 / torch.sqrt(lams)) / np.sqrt(n_pts - 1))
-        Utmu = U.t() @ mu
-        self._save(U=U.cpu().numpy(), lams=lams.cpu().numpy(), mu=mu.cpu().numpy(), Utmu=Utmu.cpu().numpy())
+            coef = (U / torch.sqrt(lams).unsqueeze(0) / np.sqrt(n_pts - 1)).t().contiguous()     # [P, pts]
+            U = eng.gemm_nt(rows.t().contiguous(), coef, mode=CONV_SIMT_FP32)                     # X V, [dims, P]
+        Utmu = eng.gemm_nt(U.t().contiguous(), mu_row.contiguous(), mode=CONV_SIMT_FP32)          # [P, 1]
+        self._save(U=U.cpu().numpy(), lams=lams.cpu().numpy(), mu=mu_row.t().cpu().numpy(), Utmu=Utmu.cpu().numpy())
 
     def load(self, gpu=None):
         """pca.py:86-106: W = (U diag(lams^-1/2))^T as [P, D, 1, 1], b = -W mu, on the GPU."""

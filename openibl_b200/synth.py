@@ -114,6 +114,33 @@ def make_images(seed: int, batch: int, height: int = 480, width: int = 640) -> t
     return torch.randn(batch, 3, height, width, generator=_gen(seed))
 
 
+def make_smooth_images(seed: int, batch: int, height: int, width: int, amp: float = 2.0) -> torch.Tensor:
+    """Smooth random fields (a 3 x H/16 x W/16 normal sample upsampled bilinearly): unlike white noise they give
+    clearly different descriptors through a random-init trunk (used where similarities must not all be ~1)."""
+    c = torch.randn(batch, 3, max(height // 16, 2), max(width // 16, 2), generator=_gen(seed))
+    return torch.nn.functional.interpolate(c, size=(height, width), mode="bilinear", align_corners=False) * amp
+
+
+def make_sfrs_tuples(seed: int, tuples: int, neg_num: int, n_diff: int, height: int, width: int):
+    """(inputs_easy [B, neg_num+2, 3,H,W], inputs_diff [B, 1+n_diff, 3,H,W]) as SFRSTrainer._parse_data produces them
+    (trainers.py:228-233): anchor, its positive (anchor + noise), negatives (other places); the difficult positives
+    are noisier views of the anchor."""
+    g = _gen(seed + 77)
+    per = 1 + neg_num
+    fields = make_smooth_images(seed, tuples * per, height, width).view(tuples, per, 3, height, width)
+    noise = lambda s: s * torch.randn(tuples, 3, height, width, generator=g)
+    anchor = fields[:, 0]
+    negs = []
+    for i in range(neg_num):           # negative i: another place whose quadrant i % 4 shows the anchor's scene, so its
+        n = fields[:, 1 + i].clone()   # best-matching REGION is a quarter, not the whole image (exercises trainers.py:261-271)
+        h0, w0 = (i % 4 // 2) * (height // 2), (i % 2) * (width // 2)
+        n[:, :, h0:h0 + height // 2, w0:w0 + width // 2] = anchor[:, :, h0:h0 + height // 2, w0:w0 + width // 2]
+        negs.append(n)
+    easy = torch.stack([anchor, anchor + noise(0.4)] + negs, dim=1)
+    diff = torch.stack([anchor] + [anchor + noise(0.9) for _ in range(n_diff)], dim=1)
+    return easy.contiguous(), diff.contiguous()
+
+
 def make_gallery(n_db: int, n_q: int, dim: int = 4096, sigma: float = 0.25,
                  seed_db: int = 2, seed_q: int = 3):
     """Pitts-shaped synthetic retrieval set.

@@ -86,12 +86,15 @@ def test_reference_examples_test_py_runs_unmodified_and_matches_oracle(tmp_path)
     script = str(tmp_path / "test.py")
     with open(script, "wb") as f:
         f.write(open(FIXTURE, "rb").read())
-    env = dict(os.environ, IBL_VGG16_RANDOM_INIT_OK="1")    # models.create('vgg16') defaults to pretrained=True (a download)
+    # models.create('vgg16') defaults to pretrained=True (a download); PYTHONPATH = this repository's `ibl` + the empty
+    # h5py stand-in (inherited by the spawned DataLoader workers, which re-import the script)
+    env = dict(os.environ, IBL_VGG16_RANDOM_INIT_OK="1",
+               PYTHONPATH=os.pathsep.join([ROOT, os.path.join(ROOT, "tests", "fixtures", "stubs"),
+                                           os.environ.get("PYTHONPATH", "")]))
     nproc = 2 if torch.cuda.device_count() >= 2 else 1
     cmd = [sys.executable, "-m", "torch.distributed.run", "--nnodes=1", f"--nproc-per-node={nproc}",
            "--master-addr", "127.0.0.1", "--master-port", "29741",
-           os.path.join(ROOT, "tests", "fixtures", "run_unmodified.py"), script,
-           "--launcher", "pytorch", "-d", "pitts", "--scale", "30k", "--data-dir", data_dir, "--resume", ckpt,
+           script, "--launcher", "pytorch", "-d", "pitts", "--scale", "30k", "--data-dir", data_dir, "--resume", ckpt,
            "--vlad", "--reduction", "--features", str(FEATURES), "--height", str(H), "--width", str(W),
            "--test-batch-size", "8", "-j", "2"]
     out = subprocess.run(cmd, capture_output=True, text=True, timeout=900, cwd=str(tmp_path), env=env)

@@ -106,3 +106,24 @@ def test_config4_gallery_ranking_is_world_size_independent():
     if torch.cuda.device_count() >= 2:
         two = _gallery([], nproc=2)
         assert two["topk_index_hash"] == one["topk_index_hash"] and two["recalls"] == one["recalls"], (two, one)
+
+
+def test_sfrs_step_under_ddp_matches_reference_loss():
+    """BASELINE configs[4]: one SFRS step (trainers.py:235-259) under torch.distributed.run + DistributedDataParallel
+    over NCCL, on every GPU of the box (8 on the scaling box, 1 here if there is one): rank 0's losses equal the
+    unmodified reference's CPU losses on the same tuples (tests/golden/sfrs_step.npz), gradients are finite, and all
+    ranks hold identical parameters after the optimizer step."""
+    import json
+    from conftest import load_golden
+    g = load_golden("sfrs_step")
+    nproc = max(1, min(8, torch.cuda.device_count()))
+    cmd = [sys.executable, "-m", "torch.distributed.run", "--nnodes=1", f"--nproc-per-node={nproc}", "--master-addr",
+           "127.0.0.1", "--master-port", "29751", os.path.join(ROOT, "examples", "sfrs_step_synthetic.py"),
+           "--launcher", "pytorch", "--tuple-size", "2", "--neg-num", "2", "--diff-num", "2", "--height", "64", "--width", "96",
+           "--generation", "0", "--seed", "31"]
+    out = subprocess.run(cmd, capture_output=True, text=True, timeout=900, cwd=ROOT)
+    assert out.returncode == 0, out.stdout[-2000:] + out.stderr[-2000:]
+    r = json.loads([l for l in out.stdout.splitlines() if l.startswith("SFRS_STEP ")][-1][len("SFRS_STEP "):])
+    assert r["world"] == nproc and r["finite"] and r["params_identical_across_ranks"] and r["grad_norm_rank0"] > 0
+    assert abs(r["loss_hard"] - float(g["g0_loss_hard"])) < 2e-4 and abs(r["loss_soft"] - float(g["g0_loss_soft"])) < 6e-4
+    assert r["trainable_params"] == 3 * (512 * 512 * 9 + 512) + 2 * 64 * 512

@@ -389,22 +389,29 @@ def test_pca_fit_load_infer_roundtrip_vs_oracle(eng, O, tmp_path):
     through sign-invariant quantities: |y| per component and all pairwise distances."""
     from openibl_b200.pca import PCA
     gen = torch.Generator().manual_seed(31)
-    n_pts, n_dims, P = 700, 512, 64
-    basis = torch.randn(n_dims, n_dims, generator=gen)
-    x = (torch.randn(n_pts, n_dims, generator=gen) * torch.logspace(0, -2, n_dims)) @ basis
-    x = torch.nn.functional.normalize(x + 0.1 * torch.randn(n_dims, generator=gen), dim=1)
-    pca = PCA(pca_n_components=P, pca_whitening=True, pca_parameters_path=str(tmp_path / "pca.h5"))
-    pca.train(x.cuda())
-    pca.load(gpu=0)
-    assert tuple(pca.weight.shape) == (P, n_dims, 1, 1) and tuple(pca.bias.shape) == (P,)
-    q = x[:50].cuda()
-    got = pca.infer(q).cpu()
-    U, lams, mu, _ = O.pca_train(x.clone(), n_components=P)
-    w, b = O.pca_load(U, lams, mu, n_components=P)
-    want = O.pca_whiten(x[:50], w, b)
-    assert rel_l2(got.abs(), want.abs()) < 2e-3, rel_l2(got.abs(), want.abs())
-    dg, dw = torch.cdist(got.double(), got.double()), torch.cdist(want.double(), want.double())
-    assert float((dg - dw).abs().max()) < 2e-3
+    # covariance branch (n_dims <= n_pts) and dual branch (n_dims > n_pts, what examples/test.py:108-121 hits with
+    # 10k x 32768 descriptors); both on the engine's fp32 GEMM (ibl_gemm_nt) + torch.linalg.eigh
+    for n_pts, n_dims, P in ((700, 512, 64), (150, 1024, 32)):
+        basis = torch.randn(n_dims, n_dims, generator=gen)
+        x = (torch.randn(n_pts, n_dims, generator=gen) * torch.logspace(0, -2, n_dims)) @ basis
+        x = torch.nn.functional.normalize(x + 0.1 * torch.randn(n_dims, generator=gen), dim=1)
+        pca = PCA(pca_n_components=P, pca_whitening=True, pca_parameters_path=str(tmp_path / f"pca{n_pts}.h5"))
+        pca.train(x.cuda())
+        pca.load(gpu=0)
+        assert tuple(pca.weight.shape) == (P, n_dims, 1, 1) and tuple(pca.bias.shape) == (P,)
+        q = x[:50].cuda()
+        got = pca.infer(q).cpu()
+        U, lams, mu, _ = O.pca_train(x.clone(), n_components=P)
+        w, b = O.pca_load(U, lams, mu, n_components=P)
+        want = O.pca_whiten(x[:50], w, b)
+        assert rel_l2(got.abs(), want.abs()) < 2e-3, (n_pts, rel_l2(got.abs(), want.abs()))
+        dg, dw = torch.cdist(got.double(), got.double()), torch.cdist(want.double(), want.double())
+        assert float((dg - dw).abs().max()) < 2e-3
+    # the GEMM entry point itself, both math modes, ragged inner dimension (zero-padded to 64)
+    a, bm = torch.randn(70, 333, generator=gen), torch.randn(45, 333, generator=gen)
+    for mode, tol in ((0, 2e-6), (1, 2e-5)):
+        c = eng.gemm_nt(a.cuda(), bm.cuda(), alpha=0.5, mode=mode).cpu()
+        assert rel_l2(c, 0.5 * (a.double() @ bm.double().t())) < tol, mode
 
 
 def test_pca_full_size_vs_oracle(eng, O):
@@ -688,3 +695,55 @@ def test_evaluate_all_large_k_and_engine_cache_invalidation(eng, O):
     with torch.no_grad():
         want = O.embednetpca_forward(x.cpu(), sd2)
     assert rel_l2(b.cpu(), want) < DESC_TOL
+
+
+def test_descriptor_is_bit_identical_across_batch_compositions(eng):
+    """An image's descriptor must not depend on the batch it travels in (tile shapes, NetVLAD units per image and
+    PCA split-K are functions of the image size only): that is what makes the 250k gallery rank identically on 1 and
+    8 GPUs, whose slices end in different tail batches."""
+    sd = synth.make_state_dict(seed=2, sharp=True, with_pca=True, pca_dim=256, bias_scale=0.02)
+    _bind(eng, sd)
+    for (h, w) in ((64, 96), (480, 640)):
+        n = 37 if h == 64 else 33
+        x = synth.make_images(seed=50, batch=n, height=h, width=w).cuda()
+        full, _ = eng.extract(x, pca=True)
+        full_v, _ = eng.extract(x, pca=False)
+        for lo, hi in ((0, 1), (3, 10), (n - 18, n)):
+            part, _ = eng.extract(x[lo:hi].contiguous(), pca=True)
+            part_v, _ = eng.extract(x[lo:hi].contiguous(), pca=False)
+            assert torch.equal(part_v, full_v[lo:hi]), (h, lo, hi, "vlad")
+            assert torch.equal(part, full[lo:hi]), (h, lo, hi, "pca")
+
+
+def test_single_pass_screening_guard_and_exact_fallback(eng, O):
+    """The distance/top-k path screens with ONE fp16 tensor-core pass and decides in exact fp32.  (a) On descriptor-like
+    data the guard never fires and the ranking equals the oracle's.  (b) On an adversarial database -- 40 near-copies
+    of every query's positive, 1e-6 apart, far more than the 16 survivors a query keeps -- the guard must fire, and
+    the exact brute-force fallback must give the oracle's ranking (fp32 distances, ties to the lowest index)."""
+    q, db, gt = synth.make_gallery(n_db=5000, n_q=300, dim=512, sigma=0.28)
+    d = O.pairwise_distance(q, db).numpy()
+    wd, wi = O.topk_from_distmat(d, 10)
+    dk, ik = eng.l2dist_topk(q.cuda(), db.cuda(), 10)
+    assert eng.dist_flagged() == 0
+    assert np.array_equal(ik.cpu().numpy(), wi) and np.allclose(dk.cpu().numpy(), wd, atol=2e-5)
+    # adversarial: clusters of near-duplicates
+    gen = torch.Generator().manual_seed(3)
+    centers = torch.nn.functional.normalize(torch.randn(60, 256, generator=gen), dim=1)
+    db2 = (centers.repeat_interleave(40, dim=0) + 1e-6 * torch.randn(2400, 256, generator=gen)).contiguous()
+    q2 = torch.nn.functional.normalize(centers.repeat(3, 1) + 0.05 * torch.randn(180, 256, generator=gen), dim=1).contiguous()
+    d2 = O.pairwise_distance(q2, db2).numpy()
+    dk2, ik2 = eng.l2dist_topk(q2.cuda(), db2.cuda(), 10, idx_base=7)
+    flagged = eng.dist_flagged()
+    assert flagged > 0, "the guard must notice that 16 survivors cannot cover 40 near-ties"
+    got_d, got_i = dk2.cpu().numpy(), ik2.cpu().numpy() - 7
+    # distances are exact fp32 either way; indices may differ from the fp32-GEMM oracle only inside exact ties
+    wd2, wi2 = O.topk_from_distmat(d2, 10)
+    assert np.allclose(got_d, wd2, atol=3e-6)
+    eng.set_gemm_mode(0)                                       # fp32 CUDA-core path: same arithmetic family as the fallback
+    dk3, ik3 = eng.l2dist_topk(q2.cuda(), db2.cuda(), 10, idx_base=7)
+    eng.set_gemm_mode(1)
+    assert np.allclose(got_d, dk3.cpu().numpy(), atol=3e-6)
+    # every returned neighbour really has the distance it claims (exact fp64 check) and belongs to the right cluster
+    exact = ((q2.double().unsqueeze(1) - db2.double()[torch.from_numpy(got_i)]) ** 2).sum(-1).numpy()
+    assert np.abs(exact - got_d).max() < 5e-6
+    assert (got_i // 40 == (np.arange(180) % 60)[:, None]).all()
