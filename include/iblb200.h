@@ -160,6 +160,14 @@ int ibl_extract_host(ibl_engine* e, const float* x_nchw_host, int N, int H, int 
  * mean3/std3 HOST float[3], out device fp32 [N,3,H,W]. */
 int ibl_preprocess_u8(ibl_engine* e, const uint8_t* x_nhwc, int N, int H, int W, const float* mean3,
                       const float* std3, float* out_nchw, void* stream);
+/* T.Resize((H, W)) on a PIL image (the first stage of the reference's test transform, utils/data/__init__.py:37-42):
+ * Pillow's 8-bit bilinear resample (antialiased, fixed point, horizontal pass then vertical pass), bit-exact.
+ * x [N,Hin,Win,3] -> out [N,Hout,Wout,3], device uint8.  bounds_* [out,2] (first sample, count) and kk_* [out,ksize]
+ * (coefficients with 22 fractional bits) are DEVICE int32 tables built by the host as Pillow's precompute_coeffs /
+ * normalize_coeffs_8bpc do (openibl_b200/utils/data/gpu_resize.py); a pass whose sizes are equal is skipped. */
+int ibl_resize_bilinear_u8(ibl_engine* e, const uint8_t* x_nhwc, int N, int Hin, int Win, int Hout, int Wout,
+                           const int* bounds_h, const int* kk_h, int ksize_h, const int* bounds_v, const int* kk_v,
+                           int ksize_v, uint8_t* out_nhwc, void* stream);
 /* ibl_extract_host for a loader that hands over decoded uint8 HWC images (Preprocessor.__getitem__,
  * ibl/utils/data/preprocessor.py:31-42, minus the CPU transform): H2D of N*H*W*3 bytes (a quarter of the fp32
  * tensor), the transform above on the device, the extraction path, D2H of the descriptors, stream sync. */
@@ -187,6 +195,9 @@ int ibl_l2dist_topk(ibl_engine* e, const float* q, int m, const float* db, int n
  * from np.argsort (evaluators.py:143,151-159).  Same ordering rule as ibl_l2dist_topk.  1 <= k <= 1024. */
 int ibl_topk_rows(ibl_engine* e, const float* dist, int m, int n, int k, float* out_dist,
                   int64_t* out_idx, void* stream);
+/* torch.argsort(distmat, dim=1) of the training samplers' refresh (ibl/utils/data/sampler.py:46-54,126-135) on the
+ * device: dist [m,n] -> out_idx [m,n], every row ascending by (distance, index). */
+int ibl_argsort_rows(ibl_engine* e, const float* dist, int m, int n, int64_t* out_idx, void* stream);
 /* k-way merge of per-shard candidates (after the NCCL all-gather): cand_* [parts,m,k_in]
  * -> out_* [m,k_out] ascending by (dist, idx). Entries with idx < 0 are ignored. */
 int ibl_topk_merge(ibl_engine* e, const float* cand_dist, const int64_t* cand_idx, int parts,

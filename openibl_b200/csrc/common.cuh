@@ -102,6 +102,13 @@ int launch_conv3x3_tc(const __nv_bfloat16* x_hi, const __nv_bfloat16* x_lo, cons
 int launch_maxpool2x2_planes(const __nv_bfloat16* hi, const __nv_bfloat16* lo, int N, int H, int W,
                              int C, __nv_bfloat16* yhi, __nv_bfloat16* ylo, cudaStream_t s);
 int tc_selftest(float* max_rel_err, cudaStream_t s);
+// sort_rows.cu  (full argsort of distance-matrix rows: the training samplers' mining)
+int launch_argsort_rows(const float* dist, long long ld, int m, int n, long long* idx, unsigned long long* scratch,
+                        cudaStream_t s, uint64_t* launches);
+// resize.cu  (Pillow-exact 8-bit bilinear resample)
+int launch_resize_bilinear_u8(const uint8_t* x, int N, int Hin, int Win, int Hout, int Wout, const int* bounds_h,
+                              const int* kk_h, int ksize_h, const int* bounds_v, const int* kk_v, int ksize_v,
+                              uint8_t* tmp, uint8_t* out, cudaStream_t s, uint64_t* launches);
 // tc_conv_bwd.cu  (dgrad filter re-layout, tcgen05 wgrad, ReLU mask, pool backward, conv1_1 wgrad)
 int launch_repack_weights_dgrad(const float* w_tck, int cout, int cin, __nv_bfloat16* w_hi, __nv_bfloat16* w_lo,
                                 cudaStream_t s);

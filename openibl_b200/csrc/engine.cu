@@ -700,6 +700,26 @@ int ibl_preprocess_u8(ibl_engine* e, const uint8_t* x_nhwc, int N, int H, int W,
   return launch_u8_hwc_to_nchw_norm(x_nhwc, N, H, W, mean3, std3, out_nchw, S(stream));
 }
 
+// T.Resize((H, W)) of the reference's test transform (ibl/utils/data/__init__.py:37-42) on decoded uint8 HWC batches,
+// bit-exact with Pillow's bilinear resample.  bounds_* [out,2] and kk_* [out,ksize] are DEVICE int32 tables built by
+// the host exactly as Pillow builds them (openibl_b200/utils/data/gpu_resize.py); a pass with equal sizes is skipped.
+int ibl_resize_bilinear_u8(ibl_engine* e, const uint8_t* x_nhwc, int N, int Hin, int Win, int Hout, int Wout,
+                           const int* bounds_h, const int* kk_h, int ksize_h, const int* bounds_v, const int* kk_v,
+                           int ksize_v, uint8_t* out_nhwc, void* stream) {
+  IBL_REQUIRE(e && x_nhwc && out_nhwc, "null argument");
+  IBL_REQUIRE(N >= 1 && Hin >= 1 && Win >= 1 && Hout >= 1 && Wout >= 1, "empty image batch");
+  IBL_REQUIRE(Wout == Win || (bounds_h && kk_h && ksize_h >= 1), "horizontal pass needs its coefficient table");
+  IBL_REQUIRE(Hout == Hin || (bounds_v && kk_v && ksize_v >= 1), "vertical pass needs its coefficient table");
+  DeviceGuard g(e->device);
+  uint8_t* tmp = nullptr;
+  if (Wout != Win && Hout != Hin) {
+    IBL_RET(e->stage_u8.ensure((size_t)N * Hin * Wout * 3));
+    tmp = e->stage_u8.as<uint8_t>();
+  }
+  return launch_resize_bilinear_u8(x_nhwc, N, Hin, Win, Hout, Wout, bounds_h, kk_h, ksize_h, bounds_v, kk_v, ksize_v, tmp,
+                                   out_nhwc, S(stream), &e->launches);
+}
+
 int ibl_extract_host_u8(ibl_engine* e, const uint8_t* x_nhwc_host, int N, int H, int W, const float* mean3,
                         const float* std3, unsigned flags, float* out_host, float* pool_host, void* stream) {
   IBL_REQUIRE(e && x_nhwc_host && mean3 && std3 && out_host, "null argument");
@@ -968,6 +988,20 @@ int ibl_topk_rows(ibl_engine* e, const float* dist, int m, int n, int k, float* 
   DeviceGuard g(e->device);
   e->launches++;
   return launch_topk_rows(dist, n, m, n, k, 0, out_dist, out_idx, false, S(stream));
+}
+
+// torch.argsort(distmat, dim=1) of the training samplers (ibl/utils/data/sampler.py:46-54,126-135) on the device:
+// dist [m,n] -> out_idx [m,n], ascending by (distance, index).
+int ibl_argsort_rows(ibl_engine* e, const float* dist, int m, int n, int64_t* out_idx, void* stream) {
+  IBL_REQUIRE(e && dist && out_idx, "null argument");
+  IBL_REQUIRE(m >= 0 && n >= 1, "bad shape");
+  DeviceGuard g(e->device);
+  unsigned long long* scratch = nullptr;
+  if (n > 16384) {
+    IBL_RET(e->dist_chunk.ensure((size_t)2 * m * n * sizeof(unsigned long long)));
+    scratch = e->dist_chunk.as<unsigned long long>();
+  }
+  return launch_argsort_rows(dist, n, m, n, reinterpret_cast<long long*>(out_idx), scratch, S(stream), &e->launches);
 }
 
 int ibl_topk_merge(ibl_engine* e, const float* cand_dist, const int64_t* cand_idx, int parts, int m,

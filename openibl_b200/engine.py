@@ -269,6 +269,39 @@ class Engine:
               "ibl_preprocess_u8")
         return out
 
+    def resize_u8(self, x_u8_nhwc: torch.Tensor, out_h: int, out_w: int) -> torch.Tensor:
+        """uint8 [N,H,W,3] on the GPU -> uint8 [N,out_h,out_w,3], bit-identical to PIL.Image.resize(..., BILINEAR)."""
+        from .utils.data.gpu_resize import pil_bilinear_coeffs
+        x = _require_cuda(x_u8_nhwc, "images", dtype=torch.uint8)
+        N, H, W, C = x.shape
+        assert C == 3
+        tabs = self._keep.setdefault("resize_tabs", {})
+
+        def table(n_in, n_out):
+            if n_in == n_out:
+                return None, None, 0
+            key = (n_in, n_out)
+            if key not in tabs:
+                b, k, ks = pil_bilinear_coeffs(n_in, n_out)
+                tabs[key] = (torch.from_numpy(b).to(x.device), torch.from_numpy(k).to(x.device), ks)
+            return tabs[key]
+
+        bh, kh, ksh = table(W, out_w)
+        bv, kv, ksv = table(H, out_h)
+        out = torch.empty(N, out_h, out_w, 3, dtype=torch.uint8, device=x.device)
+        check(self.lib.ibl_resize_bilinear_u8(self.h, _ptr(x), N, H, W, int(out_h), int(out_w), _ptr(bh), _ptr(kh), ksh,
+                                              _ptr(bv), _ptr(kv), ksv, _ptr(out), _stream(self.device)),
+              "ibl_resize_bilinear_u8")
+        return out
+
+    def argsort_rows(self, dist: torch.Tensor) -> torch.Tensor:
+        """torch.argsort(dist, dim=1) on the engine's own sort kernels: [m,n] fp32 -> [m,n] int64, ties by index."""
+        dist = _require_cuda(dist, "distance matrix")
+        m, n = dist.shape
+        out = torch.empty(m, n, dtype=torch.int64, device=dist.device)
+        check(self.lib.ibl_argsort_rows(self.h, _ptr(dist), m, n, _ptr(out), _stream(self.device)), "ibl_argsort_rows")
+        return out
+
     def extract_host_u8(self, x_u8_host: torch.Tensor, out_host: torch.Tensor, mean, std, pca=False,
                         pool_host: Optional[torch.Tensor] = None) -> torch.Tensor:
         """HOST uint8 [N,H,W,3] in / HOST descriptors out: a quarter of extract_host's H2D bytes."""

@@ -747,3 +747,56 @@ def test_single_pass_screening_guard_and_exact_fallback(eng, O):
     exact = ((q2.double().unsqueeze(1) - db2.double()[torch.from_numpy(got_i)]) ** 2).sum(-1).numpy()
     assert np.abs(exact - got_d).max() < 5e-6
     assert (got_i // 40 == (np.arange(180) % 60)[:, None]).all()
+
+
+def test_gpu_resize_matches_pillow_bit_exact(eng):
+    """T.Resize((H, W)) of the reference's test transform (utils/data/__init__.py:37-42) on the GPU,
+    bit-identical to PIL.Image.resize(..., BILINEAR): down- and up-scaling, odd sizes, one-axis-only, identity, and
+    then ToTensor + Normalize on the device equal to the torchvision pipeline on the CPU."""
+    from PIL import Image
+    import torchvision.transforms as T
+    from openibl_b200.utils.data import _MEAN, _STD, get_transformer_test
+    rng = np.random.RandomState(0)
+    for (h, w, oh, ow) in ((120, 160, 96, 128), (37, 53, 64, 96), (480, 640, 480, 640), (300, 451, 480, 640),
+                           (768, 1024, 480, 640), (50, 50, 17, 200), (90, 128, 96, 128), (96, 130, 96, 128)):
+        imgs = rng.randint(0, 256, size=(3, h, w, 3)).astype(np.uint8)
+        want = np.stack([np.asarray(Image.fromarray(im).resize((ow, oh), Image.BILINEAR)) for im in imgs])
+        got = eng.resize_u8(torch.from_numpy(imgs).cuda(), oh, ow)
+        assert torch.equal(got.cpu(), torch.from_numpy(want)), (h, w, oh, ow)
+    tf = get_transformer_test(96, 128)
+    ref = torch.stack([tf(Image.fromarray(im)) for im in imgs])
+    dev = eng.preprocess_u8(eng.resize_u8(torch.from_numpy(imgs).cuda(), 96, 128), _MEAN, _STD)
+    assert torch.equal(dev.cpu(), ref)
+
+
+def test_device_argsort_rows_and_sampler_refresh(eng):
+    """the samplers' `torch.argsort(distmat, dim=1)` (sampler.py:49,129) on the device -- short rows
+    (shared-memory bitonic), long rows (chunk sort + merge passes), exact ties -- and the tuple samplers refreshed
+    through it yield the reference's tuples (tests/golden/sampler.npz)."""
+    import random
+    from ibl.utils.data.sampler import DistributedRandomTupleSampler, DistributedRandomDiffTupleSampler
+    gen = torch.Generator().manual_seed(1)
+    for (m, n) in ((5, 1), (7, 150), (3, 10000), (2, 16384), (3, 16385), (2, 70001)):
+        d = torch.rand(m, n, generator=gen)
+        d[:, n // 3] = d[:, n // 2]                                   # a tie per row
+        want = torch.argsort(d, dim=1, stable=True)
+        got = eng.argsort_rows(d.cuda()).cpu()
+        assert torch.equal(got, want), (m, n)
+    g = load_golden("sampler")
+    NQ, NG = g["dist"].shape
+    q = [("q%03d" % i, i, 0.0, 0.0) for i in range(NQ)]
+    gal = [("g%03d" % i, 1000 + i, 0.0, 0.0) for i in range(NG)]
+    pos_l, neg_l = [p.tolist() for p in g["pos"]], [sorted(set(n.tolist())) for n in g["neg"]]
+    sub = list(range(3, NQ, 2))
+    for name, cls, kw in (("tuple", DistributedRandomTupleSampler, dict(neg_num=4, neg_pool=30)),
+                          ("diff", DistributedRandomDiffTupleSampler, dict(pos_num=3, pos_pool=5, neg_num=4, neg_pool=30))):
+        s = cls(q, gal, pos_l, neg_l, num_replicas=2, rank=1, **kw)
+        random.seed(12)
+        if name == "tuple":
+            s.sort_gallery(torch.from_numpy(g["dist"]), sub)
+        else:
+            s.sort_gallery(torch.from_numpy(g["dist"]).cuda(), torch.from_numpy(g["jac"]), sub)
+        assert torch.equal(s.sort_idx, torch.from_numpy(g["sort_idx"]))
+        for ep in (0, 1):
+            got = np.asarray([r + [-1] * (9 - len(r)) for r in iter(s)], dtype=np.int64)
+            assert np.array_equal(got, g[f"{name}_r1_e{ep}"]), (name, ep)

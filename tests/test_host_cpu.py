@@ -278,3 +278,35 @@ def test_sfrs_loss_algebra_matches_reference_golden():
     assert abs(got.item() - float(g["u_hard_loss"])) < 2e-6
     with pytest.raises(ValueError):
         tr._get_loss(a, p, n, 4, "nope")
+
+
+def _sampler_fixture():
+    g = load_golden("sampler")
+    NQ, NG = g["dist"].shape
+    q = [("q%03d" % i, i, 0.0, 0.0) for i in range(NQ)]
+    gal = [("g%03d" % i, 1000 + i, 0.0, 0.0) for i in range(NG)]
+    pos_l = [p.tolist() for p in g["pos"]]
+    neg_l = [sorted(set(n.tolist())) for n in g["neg"]]
+    return g, q, gal, pos_l, neg_l, list(range(3, NQ, 2))
+
+
+def test_tuple_samplers_yield_reference_tuples_given_the_reference_ranking():
+    """DistributedRandomTupleSampler / DistributedRandomDiffTupleSampler (sampler.py:15-192): with the same ranking
+    and the same `random` state the host logic yields exactly the reference's tuples, over two epochs (cached hard
+    negatives) and two ranks.  The ranking itself comes from the device argsort on the GPU (test_gpu_parity)."""
+    import random
+    from ibl.utils.data.sampler import DistributedRandomTupleSampler, DistributedRandomDiffTupleSampler
+    g, q, gal, pos_l, neg_l, sub = _sampler_fixture()
+    for name, cls, kw in (("tuple", DistributedRandomTupleSampler, dict(neg_num=4, neg_pool=30)),
+                          ("diff", DistributedRandomDiffTupleSampler, dict(pos_num=3, pos_pool=5, neg_num=4, neg_pool=30))):
+        for rank in (0, 1):
+            s = cls(q, gal, pos_l, neg_l, num_replicas=2, rank=rank, **kw)
+            random.seed(11 + rank)
+            s.sort_idx, s.sub_set, s.sub_length = torch.from_numpy(g["sort_idx"]), sub, len(sub)
+            s._resize()
+            if name == "diff":
+                s.distmat_jac = torch.from_numpy(g["jac"])
+            assert len(s) == int(g[f"{name}_len"])
+            for ep in (0, 1):
+                got = np.asarray([r + [-1] * (9 - len(r)) for r in iter(s)], dtype=np.int64)   # ragged rows padded with -1
+                assert np.array_equal(got, g[f"{name}_r{rank}_e{ep}"]), (name, rank, ep)
