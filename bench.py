@@ -337,18 +337,28 @@ def main():
         else:
             shapes.append((hh, ww, item[1], item[2]))
     conv_ms, conv_gflop = 0.0, 0.0
+    fused1 = os.environ.get("IBL_CONV1_FUSED", "1") != "0"
     for li, (lh, lw, cin, cout) in enumerate(shapes):
-        if li == 0:
-            continue
-        xin = torch.randn(BATCH, lh, lw, cin, device=dev).relu_()
+        if li == 0 and not fused1:
+            continue                      # conv1_1 alone (Cin = 3, output-write bound) is not part of the family
+        if li == 1 and fused1:
+            continue                      # conv1_2 is inside the fused conv1 kernel timed at li == 0
         msl = ctypes.c_float()
-        check(eng.lib.ibl_debug_time_layer(eng.h, li, _ptr(xin), BATCH, lh, lw, 0, 3, ctypes.byref(msl)), "time_layer")
+        if li == 0:                       # conv1_1 + conv1_2 + pool in ONE kernel: layer id 13, NCHW image input
+            check(eng.lib.ibl_debug_time_layer(eng.h, 13, _ptr(xs[0]), BATCH, lh, lw, 0, 3, ctypes.byref(msl)), "time_layer")
+            conv_gflop += 2.0 * BATCH * lh * lw * 9 * (3 * 64 + 64 * 64) / 1e9
+        else:
+            xin = torch.randn(BATCH, lh, lw, cin, device=dev).relu_()
+            check(eng.lib.ibl_debug_time_layer(eng.h, li, _ptr(xin), BATCH, lh, lw, 0, 3, ctypes.byref(msl)), "time_layer")
+            conv_gflop += 2.0 * BATCH * lh * lw * 9 * cin * cout / 1e9
+            del xin
         conv_ms += msl.value
-        conv_gflop += 2.0 * BATCH * lh * lw * 9 * cin * cout / 1e9
-        del xin
     ach_k = conv_gflop / conv_ms
     conv_traffic = load_conv_traffic()
-    roofline = {"bound": "tensor", "kernel": "conv3x3_tc_kernel (12 launches: conv1_2..conv5_3, tcgen05 implicit GEMM, bf16x3)",
+    roofline = {"bound": "tensor",
+                "kernel": ("conv1_fused_tc_kernel (conv1_1+conv1_2+pool) + conv3x3_tc_kernel x 11 (conv2_1..conv5_3): 12 launches, "
+                           "tcgen05 implicit GEMM, bf16x3") if fused1 else
+                          "conv3x3_tc_kernel (12 launches: conv1_2..conv5_3, tcgen05 implicit GEMM, bf16x3)",
                 "achieved": ach_k, "peak": pk["bf16_tflops_sustained"], "unit": "TFLOP/s",
                 "frac": ach_k / pk["bf16_tflops_sustained"],
                 "traffic": conv_traffic.get("dram_bytes_per_step"), "traffic_note": conv_traffic.get("note"),

@@ -99,6 +99,8 @@ int launch_conv3x3_tc(const __nv_bfloat16* x_hi, const __nv_bfloat16* x_lo, cons
                       int N, int H, int W, int cin, int cout, bool relu, bool pool,
                       __nv_bfloat16* y_hi, __nv_bfloat16* y_lo, float* y_f32, cudaStream_t s,
                       float* ssq = nullptr, int* ssq_parts = nullptr);
+int launch_conv1_fused_tc(const float* x_nchw, const float* w1_oihw, const float* bias1, const ConvParams& p2, int N, int H,
+                          int W, __nv_bfloat16* y_hi, __nv_bfloat16* y_lo, cudaStream_t s);
 int launch_maxpool2x2_planes(const __nv_bfloat16* hi, const __nv_bfloat16* lo, int N, int H, int W,
                              int C, __nv_bfloat16* yhi, __nv_bfloat16* ylo, cudaStream_t s);
 int tc_selftest(float* max_rel_err, cudaStream_t s);

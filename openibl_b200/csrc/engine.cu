@@ -153,16 +153,30 @@ int vgg_forward_impl(ibl_engine* e, const float* x, int N, int H, int W, float* 
   auto hi_of = [&](int b, size_t elems) { (void)elems; return e->act[b].as<__nv_bfloat16>(); };
   auto lo_of = [&](int b, size_t elems) { return e->act[b].as<__nv_bfloat16>() + elems; };
   size_t elems = (size_t)N * h * w * 64;
-  {
+  int first_l = 1;
+  // conv1_1 + conv1_2 + pool in one kernel (tc_conv.cu: conv1_fused_tc_kernel): the 2.5 GB conv1_1 activation never
+  // goes to HBM.  IBL_CONV1_FUSED=0 keeps the two separate kernels (A/B measurements, variant tests).
+  static const bool fused1_env = [] { const char* v = getenv("IBL_CONV1_FUSED"); return !v || atoi(v) != 0; }();
+  const bool fused1 = fused1_env && last_layer >= 2 && h >= 2 && w >= 2;
+  if (fused1) {
+    const size_t out_elems = (size_t)N * (h / 2) * (w / 2) * 64;
+    IBL_RET(launch_conv1_fused_tc(x, e->w0_oihw, e->conv[0].bias, e->conv[1], N, h, w, hi_of(1, out_elems),
+                                  lo_of(1, out_elems), s));
+    e->launches++;
+    cur = 1;
+    h /= 2;
+    w /= 2;
+    first_l = 2;
+  } else {
     static int simt1 = -1;   // IBL_CONV1_SIMT=1: keep conv1_1 on the CUDA cores (A/B experiments)
     if (simt1 < 0) { const char* v = getenv("IBL_CONV1_SIMT"); simt1 = (v && atoi(v)) ? 1 : 0; }
     if (simt1)
       IBL_RET(launch_conv1_1(x, e->conv[0], N, h, w, true, nullptr, hi_of(0, elems), lo_of(0, elems), s));
     else
       IBL_RET(launch_conv1_1_tc(x, e->w0_oihw, e->conv[0].bias, N, h, w, hi_of(0, elems), lo_of(0, elems), s));
+    e->launches++;
   }
-  e->launches++;
-  for (int l = 1; l <= last_layer; ++l) {
+  for (int l = first_l; l <= last_layer; ++l) {
     const ConvLayer& L = kVgg16[l];
     const bool last = (l == last_layer);
     const size_t in_elems = (size_t)N * h * w * L.cin;
@@ -1130,9 +1144,32 @@ int ibl_debug_umma_strided(ibl_engine* e, const void* A, int rows, const void* B
 // (x is NCHW [N,3,H,W]); layers 1..12 take x NHWC [N,H,W,Cin] fp32 (converted to planes once).
 int ibl_debug_time_layer(ibl_engine* e, int layer, const float* x, int N, int H, int W, int bn_override,
                          int reps, float* ms_out) {
-  IBL_REQUIRE(e && x && ms_out && layer >= 0 && layer < 13 && reps >= 1, "bad argument");
+  IBL_REQUIRE(e && x && ms_out && layer >= 0 && layer <= 13 && reps >= 1, "bad argument");
   if (!e->vgg_ready) { set_last_error("ibl_engine_set_vgg16 was not called"); return IBL_ERR_NOT_READY; }
   DeviceGuard g(e->device);
+  if (layer == 13) {   // the fused conv1_1 + conv1_2 + pool kernel: x is the NCHW image batch
+    const size_t out_e = (size_t)N * (H / 2) * (W / 2) * 64;
+    IBL_RET(e->act[1].ensure(out_e * 4));
+    cudaEvent_t e0, e1;
+    IBL_CUDA_OK(cudaEventCreate(&e0));
+    IBL_CUDA_OK(cudaEventCreate(&e1));
+    __nv_bfloat16* oh_ = e->act[1].as<__nv_bfloat16>();
+    int rc = IBL_OK;
+    for (int r = -1; r < reps && rc == IBL_OK; ++r) {
+      if (r == 0) cudaEventRecord(e0, nullptr);
+      rc = launch_conv1_fused_tc(x, e->w0_oihw, e->conv[0].bias, e->conv[1], N, H, W, oh_, oh_ + out_e, nullptr);
+    }
+    cudaEventRecord(e1, nullptr);
+    cudaError_t ce = cudaEventSynchronize(e1);
+    float ms = 0.f;
+    cudaEventElapsedTime(&ms, e0, e1);
+    cudaEventDestroy(e0);
+    cudaEventDestroy(e1);
+    if (rc == IBL_OK && ce != cudaSuccess) { set_last_error(cudaGetErrorString(ce)); return IBL_ERR_CUDA; }
+    *ms_out = ms / reps;
+    e->launches += reps + 1;
+    return rc;
+  }
   const ConvLayer& L = kVgg16[layer];
   const size_t in_e = (size_t)N * H * W * L.cin;
   const int oh = L.pool ? H / 2 : H, ow = L.pool ? W / 2 : W;

@@ -651,6 +651,368 @@ int launch_conv3x3_tc(const __nv_bfloat16* x_hi, const __nv_bfloat16* x_lo, cons
   return launch_tc_variant<256, 2, false>(m_xhi, m_xlo, m_whi, m_wlo, a, s);
 }
 
+// =====================================================================================================================
+// conv1_1 + conv1_2 (+ ReLU + 2x2 max-pool) in ONE kernel  (vgg.py:40-42 slots 0 and 2)
+//
+// conv1_1's output -- 64 channels at full resolution, 2.5 GB per batch of 32 as hi/lo planes -- is the largest tensor
+// of the network and was written to HBM by one kernel only to be read back by the next.  Here a CTA owns a 16 x 8
+// patch of conv1_2 outputs and RECOMPUTES the conv1_1 activations it needs, the (16+2) x (8+2) = 180-pixel halo
+// (1.06 GFLOP per image, +41 % on 180 vs 128 pixels), straight into the shared-memory halo tile that conv1_2's nine
+// tap views read (the HALO staging of conv3x3_tc_kernel, one 64-channel chunk):
+//
+//   builders (4 warps)   im2col of the 3-channel input for the 180 halo pixels: K = 27 -> 32, bf16 hi/lo, K-major
+//                        SW128 rows (two 128-row M tiles)                                   [as conv1_1_tc_kernel]
+//   MMA (1 thread)       C1: 2 M tiles x 2 K steps x 3 MMAs (M128 N64)  ->  TMEM acc1 (128 columns)
+//   epilogue 1 (4 warps) acc1 -> + bias, ReLU, ZERO outside the image (conv1_2's padding), hi/lo split -> halo tile
+//   MMA                  C2: 9 taps x 4 K steps x (A_hi.[W_hi;W_lo] N128 + A_lo.W_hi N64) -> acc2 (2 x 192 columns)
+//   epilogue 2 (4 warps) acc2 -> + bias, ReLU, 2x2 max-pool, hi/lo planes -> HBM              [conv_epilogue_tile]
+//   producer (1 thread)  TMA ring of conv1_2's weight taps (16 KiB each)
+//
+// The MMA thread issues C1 of tile i+1 BEFORE C2 of tile i, so builders and epilogue 1 of the next tile run under the
+// nine-tap main loop of the current one.  HBM traffic of the pair of layers: the 3-channel input (118 MB) + the pooled
+// output (629 MB) instead of + 2 x 2.5 GB.
+// =====================================================================================================================
+struct Conv1FusedArgs {
+  const float* x;       // [N,3,H,W]
+  const float* w1;      // conv1_1 OIHW [64,3,3,3]
+  const float* bias1;   // [64]
+  ConvTcArgs c2;        // conv1_2: N,H,W, cin = cout = 64, tw_log2 = 3, tiles, relu, pool, bias, y_hi / y_lo
+};
+
+constexpr int F1_W1 = 16384;                         // conv1_1 filters: hi 8 KiB | lo 8 KiB
+constexpr int F1_A1_PLANE = 256 * 128;               // 256 halo rows x 128 B (K = 32 uses the first 64 B of a row)
+constexpr int F1_A1 = 2 * F1_A1_PLANE;               // hi | lo
+constexpr int F1_W2_STAGE = 2 * 64 * TC_BK * 2;      // one tap of conv1_2: W_hi 8 KiB | W_lo 8 KiB
+constexpr int F1_W2_STAGES = 3;
+constexpr int F1_OFF_A1 = F1_W1;
+constexpr int F1_OFF_HALO = F1_OFF_A1 + F1_A1;       // 80 KiB, 1024-aligned
+constexpr int F1_OFF_W2 = F1_OFF_HALO + 2 * TC_HALO_STAGE;
+constexpr int F1_OFF_BAR = F1_OFF_W2 + F1_W2_STAGES * F1_W2_STAGE;
+constexpr int F1_SMEM = F1_OFF_BAR + 512 + 1024;
+static_assert(F1_SMEM <= 232448, "shared-memory budget of the fused conv1 kernel");
+
+__global__ void __launch_bounds__(448, 1)
+conv1_fused_tc_kernel(const __grid_constant__ CUtensorMap tm_whi, const __grid_constant__ CUtensorMap tm_wlo,
+                      const Conv1FusedArgs fa) {
+  extern __shared__ __align__(1024) uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  const ConvTcArgs& a = fa.c2;
+  uint8_t* w1_hi = smem;
+  uint8_t* w1_lo = smem + 8192;
+  uint8_t* a1 = smem + F1_OFF_A1;
+  uint8_t* halo = smem + F1_OFF_HALO;
+  uint8_t* w2 = smem + F1_OFF_W2;
+  uint64_t* bars = reinterpret_cast<uint64_t*>(smem + F1_OFF_BAR);
+  uint64_t* w_full = bars;                 // [3]
+  uint64_t* w_empty = bars + 3;            // [3]
+  uint64_t* a1_full = bars + 6;            // 4 builder warps
+  uint64_t* a1_empty = bars + 7;           // commit of C1
+  uint64_t* acc1_full = bars + 8;          // commit of C1
+  uint64_t* acc1_empty = bars + 9;         // 4 epilogue-1 warps
+  uint64_t* halo_full = bars + 10;         // [2] 4 epilogue-1 warps
+  uint64_t* halo_empty = bars + 12;        // [2] commit of C2
+  uint64_t* acc2_full = bars + 14;         // [2] commit of C2
+  uint64_t* acc2_empty = bars + 16;        // [2] 4 epilogue-2 warps
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 18);
+  float* bias1_s = reinterpret_cast<float*>(bars + 20);   // [64]
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  // one-time: zero A1 (the K >= 32 half of every row stays zero), lay out conv1_1's filters, zero the halo padding rows
+  for (int i = threadIdx.x; i < F1_A1 / 16; i += blockDim.x) reinterpret_cast<uint4*>(a1)[i] = make_uint4(0, 0, 0, 0);
+  for (int i = threadIdx.x; i < (2 * TC_HALO_STAGE) / 16; i += blockDim.x) reinterpret_cast<uint4*>(halo)[i] = make_uint4(0, 0, 0, 0);
+  for (int i = threadIdx.x; i < 64 * 8; i += blockDim.x) {   // (row n, chunk j): 8 k-values each, k = tap*3 + c
+    const int n = i >> 3, j = i & 7;
+    uint32_t hi[4], lo[4];
+#pragma unroll
+    for (int e = 0; e < 4; ++e) {
+      float v[2];
+#pragma unroll
+      for (int u = 0; u < 2; ++u) {
+        const int k = j * 8 + e * 2 + u;
+        v[u] = 0.f;
+        if (k < 27) v[u] = fa.w1[(n * 3 + (k % 3)) * 9 + (k / 3)];
+      }
+      const __nv_bfloat16 h0 = __float2bfloat16_rn(v[0]), h1 = __float2bfloat16_rn(v[1]);
+      __nv_bfloat162 hh(h0, h1);
+      hi[e] = *reinterpret_cast<uint32_t*>(&hh);
+      lo[e] = pack_bf16x2(v[0] - __bfloat162float(h0), v[1] - __bfloat162float(h1));
+    }
+    const int pos = n * 128 + ((j ^ (n & 7)) * 16);
+    *reinterpret_cast<uint4*>(w1_hi + pos) = make_uint4(hi[0], hi[1], hi[2], hi[3]);
+    *reinterpret_cast<uint4*>(w1_lo + pos) = make_uint4(lo[0], lo[1], lo[2], lo[3]);
+  }
+  if (threadIdx.x < 64) bias1_s[threadIdx.x] = fa.bias1[threadIdx.x];
+  if (threadIdx.x == 0) {
+    tma_prefetch_desc(&tm_whi);
+    tma_prefetch_desc(&tm_wlo);
+    for (int i = 0; i < F1_W2_STAGES; ++i) { mbar_init(&w_full[i], 1); mbar_init(&w_empty[i], 1); }
+    mbar_init(a1_full, 4); mbar_init(a1_empty, 1);
+    mbar_init(acc1_full, 1); mbar_init(acc1_empty, 4);
+    for (int i = 0; i < 2; ++i) {
+      mbar_init(&halo_full[i], 4); mbar_init(&halo_empty[i], 1);
+      mbar_init(&acc2_full[i], 1); mbar_init(&acc2_empty[i], 4);
+    }
+    fence_barrier_init();
+  }
+  if (warp == 1) { tmem_alloc(tmem_slot, 512); tmem_relinquish(); }
+  fence_proxy_async();
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+  const uint32_t t_acc1 = tmem_base + 384;            // M tile 0: columns 384-447, M tile 1: 448-511
+  constexpr uint32_t ACC2_COLS = 192;
+  const int tiles_per_img = a.tiles_h * a.tiles_w;
+  auto coords = [&](int tile, int& img, int& h0, int& w0) {
+    img = tile / tiles_per_img;
+    const int rem = tile - img * tiles_per_img;
+    h0 = (rem / a.tiles_w) * 16;
+    w0 = (rem % a.tiles_w) * 8;
+  };
+  const long long HW = (long long)a.H * a.W;
+
+  if (warp == 0) {
+    // ================= TMA producer: conv1_2 weight taps =================
+    if (lane == 0) {
+      int stage = 0; uint32_t phase = 0;
+      for (int tile = blockIdx.x; tile < a.total_tiles; tile += gridDim.x) {
+        for (int tap = 0; tap < 9; ++tap) {
+          mbar_wait(&w_empty[stage], phase ^ 1);
+          uint8_t* st = w2 + stage * F1_W2_STAGE;
+          mbar_arrive_expect_tx(&w_full[stage], F1_W2_STAGE);
+          tma_load_3d(st, &tm_whi, &w_full[stage], 0, 0, tap);
+          tma_load_3d(st + F1_W2_STAGE / 2, &tm_wlo, &w_full[stage], 0, 0, tap);
+          if (++stage == F1_W2_STAGES) { stage = 0; phase ^= 1; }
+        }
+      }
+    }
+  } else if (warp == 1) {
+    // ================= MMA issuer =================
+    if (lane == 0) {
+      constexpr uint32_t idesc64 = umma_idesc_bf16_f32(TC_BM, 64);
+      constexpr uint32_t idesc128 = umma_idesc_bf16_f32(TC_BM, 128);
+      constexpr uint64_t kHaloDesc = ((uint64_t)1 << 16) | ((uint64_t)((TC_HALO_W * 128) >> 4) << 32) |
+                                     ((uint64_t)1 << 46) | ((uint64_t)2 << 61);
+      const uint64_t b1h = umma_desc_kmajor_sw128(smem_u32(w1_hi)), b1l = umma_desc_kmajor_sw128(smem_u32(w1_lo));
+      int n_tiles = 0;
+      for (int tile = blockIdx.x; tile < a.total_tiles; tile += gridDim.x) ++n_tiles;
+      auto issue_c1 = [&](int it) {
+        mbar_wait(a1_full, it & 1);
+        mbar_wait(acc1_empty, (it & 1) ^ 1);
+        tc_fence_after();
+#pragma unroll
+        for (int mt = 0; mt < 2; ++mt) {
+          const uint32_t sa = smem_u32(a1) + mt * 16384;
+          const uint64_t ah = umma_desc_kmajor_sw128(sa), al = umma_desc_kmajor_sw128(sa + F1_A1_PLANE);
+          const uint32_t d = t_acc1 + mt * 64;
+#pragma unroll
+          for (int k = 0; k < 2; ++k) {               // K = 32: two 16-wide steps
+            const uint64_t ko = (uint64_t)(k * 2);
+            umma_bf16(d, al + ko, b1h + ko, idesc64, k > 0 ? 1u : 0u);
+            umma_bf16(d, ah + ko, b1l + ko, idesc64, 1u);
+            umma_bf16(d, ah + ko, b1h + ko, idesc64, 1u);
+          }
+        }
+        umma_commit(a1_empty);
+        umma_commit(acc1_full);
+      };
+      int stage = 0; uint32_t phase = 0;
+      if (n_tiles > 0) issue_c1(0);
+      for (int it = 0; it < n_tiles; ++it) {
+        if (it + 1 < n_tiles) issue_c1(it + 1);
+        const int hb = it & 1;
+        const uint32_t hph = (it >> 1) & 1;
+        mbar_wait(&acc2_empty[hb], hph ^ 1);
+        mbar_wait(&halo_full[hb], hph);
+        tc_fence_after();
+        const uint32_t d_tmem = tmem_base + hb * ACC2_COLS;
+        const uint32_t ha = smem_u32(halo + hb * TC_HALO_STAGE);
+        for (int tap = 0; tap < 9; ++tap) {
+          mbar_wait(&w_full[stage], phase);
+          tc_fence_after();
+          const uint32_t toff = (uint32_t)((tap / 3) * TC_HALO_W + tap % 3) * 128u;
+          const uint64_t a_hi = kHaloDesc | (uint64_t)(((ha + toff) >> 4) & 0x3fffu);
+          const uint64_t a_lo = kHaloDesc | (uint64_t)(((ha + TC_HALO_PLANE + toff) >> 4) & 0x3fffu);
+          const uint32_t sb = smem_u32(w2 + stage * F1_W2_STAGE);
+          const uint64_t b_cat = umma_desc_kmajor_sw128(sb);          // 128 rows: W_hi then W_lo
+#pragma unroll
+          for (int k = 0; k < TC_BK / 16; ++k) {
+            const uint64_t ko = (uint64_t)(k * 2);
+            const uint32_t first = (tap > 0 || k > 0) ? 1u : 0u;
+            umma_bf16(d_tmem, a_hi + ko, b_cat + ko, idesc128, first);            // [hi.hi | hi.lo]
+            umma_bf16(d_tmem + 128, a_lo + ko, b_cat + ko, idesc64, first);       // lo.hi
+          }
+          umma_commit(&w_empty[stage]);
+          if (++stage == F1_W2_STAGES) { stage = 0; phase ^= 1; }
+        }
+        umma_commit(&halo_empty[hb]);
+        umma_commit(&acc2_full[hb]);
+      }
+    }
+  } else if (warp <= 5) {
+    // ================= epilogue 2: conv1_2 accumulators -> bias, ReLU, pool, hi/lo planes =================
+    const int q = warp & 3;
+    const int m = q * 32 + lane;
+    const int r = m >> 3, c = m & 7;                  // 8-wide, 16-tall patch
+    int it = 0;
+    for (int tile = blockIdx.x; tile < a.total_tiles; tile += gridDim.x, ++it) {
+      int img, h0, w0;
+      coords(tile, img, h0, w0);
+      const int hb = it & 1;
+      mbar_wait(&acc2_full[hb], (it >> 1) & 1);
+      tc_fence_after();
+      const uint32_t t_row = tmem_base + ((uint32_t)(q * 32) << 16) + hb * ACC2_COLS;
+      conv_epilogue_tile<64, true>(a, t_row, img, h0, w0, 0, 0, r, c, 8);
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(&acc2_empty[hb]);
+    }
+  } else if (warp <= 9) {
+    // ================= epilogue 1: conv1_1 accumulators -> bias, ReLU, image mask, hi/lo -> halo tile =================
+    const int q = warp & 3;
+    int it = 0;
+    for (int tile = blockIdx.x; tile < a.total_tiles; tile += gridDim.x, ++it) {
+      int img, h0, w0;
+      coords(tile, img, h0, w0);
+      const int hb = it & 1;
+      mbar_wait(acc1_full, it & 1);
+      mbar_wait(&halo_empty[hb], ((it >> 1) & 1) ^ 1);
+      tc_fence_after();
+      uint8_t* hh = halo + hb * TC_HALO_STAGE;
+#pragma unroll 1
+      for (int mt = 0; mt < 2; ++mt) {
+        const int p = mt * 128 + q * 32 + lane;          // halo row = TMEM lane of M tile mt
+        const int hl = p / TC_HALO_W, wl = p - hl * TC_HALO_W;
+        const int ph = h0 - 1 + hl, pw = w0 - 1 + wl;
+        const bool inside = p < TC_HALO_W * TC_HALO_H && ph >= 0 && ph < a.H && pw >= 0 && pw < a.W && img < a.N;
+#pragma unroll 1
+        for (int ch = 0; ch < 2; ++ch) {
+          uint32_t raw[32];
+          tmem_ld_32x32(t_acc1 + ((uint32_t)(q * 32) << 16) + mt * 64 + ch * 32, raw);
+          tmem_ld_wait();
+          if (p < TC_HALO_W * TC_HALO_H) {
+            uint32_t hi[16], lo[16];
+#pragma unroll
+            for (int j = 0; j < 16; ++j) {
+              float x0 = fmaxf(__uint_as_float(raw[2 * j]) + bias1_s[ch * 32 + 2 * j], 0.f);
+              float x1 = fmaxf(__uint_as_float(raw[2 * j + 1]) + bias1_s[ch * 32 + 2 * j + 1], 0.f);
+              if (!inside) { x0 = 0.f; x1 = 0.f; }       // conv1_2 pads its INPUT with zeros
+              const __nv_bfloat16 h0b = __float2bfloat16_rn(x0), h1b = __float2bfloat16_rn(x1);
+              __nv_bfloat162 hv(h0b, h1b);
+              hi[j] = *reinterpret_cast<uint32_t*>(&hv);
+              lo[j] = pack_bf16x2(x0 - __bfloat162float(h0b), x1 - __bfloat162float(h1b));
+            }
+            uint8_t* rh = hh + p * 128;
+            uint8_t* rl = rh + TC_HALO_PLANE;
+#pragma unroll
+            for (int j = 0; j < 4; ++j) {
+              const int pos = ((ch * 4 + j) ^ (p & 7)) * 16;
+              *reinterpret_cast<uint4*>(rh + pos) = make_uint4(hi[4 * j], hi[4 * j + 1], hi[4 * j + 2], hi[4 * j + 3]);
+              *reinterpret_cast<uint4*>(rl + pos) = make_uint4(lo[4 * j], lo[4 * j + 1], lo[4 * j + 2], lo[4 * j + 3]);
+            }
+          }
+        }
+      }
+      tc_fence_before();
+      fence_proxy_async();                              // generic-proxy writes of the halo -> visible to the tensor core
+      __syncwarp();
+      if (lane == 0) { mbar_arrive(acc1_empty); mbar_arrive(&halo_full[hb]); }
+    }
+  } else {
+    // ================= builders: im2col rows of conv1_1 for the 180 halo pixels =================
+    const int bw = warp - 10;
+    int it = 0;
+    for (int tile = blockIdx.x; tile < a.total_tiles; tile += gridDim.x, ++it) {
+      int img, h0, w0;
+      coords(tile, img, h0, w0);
+      float v[2][32];
+#pragma unroll
+      for (int mt = 0; mt < 2; ++mt) {
+#pragma unroll
+        for (int k = 0; k < 32; ++k) v[mt][k] = 0.f;
+        const int p = mt * 128 + bw * 32 + lane;
+        const int hl = p / TC_HALO_W, wl = p - hl * TC_HALO_W;
+        const int ph = h0 - 1 + hl, pw = w0 - 1 + wl;
+        if (p < TC_HALO_W * TC_HALO_H && ph >= 0 && ph < a.H && pw >= 0 && pw < a.W && img < a.N) {
+          const float* xb = fa.x + (long long)img * 3 * HW;
+#pragma unroll
+          for (int tap = 0; tap < 9; ++tap) {
+            const int ih = ph + tap / 3 - 1, iw = pw + tap % 3 - 1;
+            if (ih >= 0 && ih < a.H && iw >= 0 && iw < a.W) {
+              const long long o = (long long)ih * a.W + iw;
+#pragma unroll
+              for (int c = 0; c < 3; ++c) v[mt][tap * 3 + c] = __ldg(xb + c * HW + o);
+            }
+          }
+        }
+      }
+      mbar_wait(a1_empty, (it & 1) ^ 1);                // C1 of the previous tile has consumed A1
+#pragma unroll
+      for (int mt = 0; mt < 2; ++mt) {
+        const int p = mt * 128 + bw * 32 + lane;
+        uint8_t* rh = a1 + p * 128;
+        uint8_t* rl = rh + F1_A1_PLANE;
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+          uint32_t hi[4], lo[4];
+#pragma unroll
+          for (int e = 0; e < 4; ++e) {
+            const float x0 = v[mt][8 * j + 2 * e], x1 = v[mt][8 * j + 2 * e + 1];
+            const __nv_bfloat16 h0b = __float2bfloat16_rn(x0), h1b = __float2bfloat16_rn(x1);
+            __nv_bfloat162 hv(h0b, h1b);
+            hi[e] = *reinterpret_cast<uint32_t*>(&hv);
+            lo[e] = pack_bf16x2(x0 - __bfloat162float(h0b), x1 - __bfloat162float(h1b));
+          }
+          const int pos = (j ^ (p & 7)) * 16;
+          *reinterpret_cast<uint4*>(rh + pos) = make_uint4(hi[0], hi[1], hi[2], hi[3]);
+          *reinterpret_cast<uint4*>(rl + pos) = make_uint4(lo[0], lo[1], lo[2], lo[3]);
+        }
+      }
+      fence_proxy_async();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(a1_full);
+    }
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 1) { tc_fence_after(); tmem_dealloc(tmem_base, 512); }
+}
+
+// x [N,3,H,W] fp32 -> conv1_1 -> ReLU -> conv1_2 -> ReLU -> 2x2 max-pool as hi/lo planes [N,H/2,W/2,64]
+int launch_conv1_fused_tc(const float* x_nchw, const float* w1_oihw, const float* bias1, const ConvParams& p2, int N, int H,
+                          int W, __nv_bfloat16* y_hi, __nv_bfloat16* y_lo, cudaStream_t s) {
+  IBL_REQUIRE(p2.w_hi && p2.w_lo && p2.bias, "fused conv1: conv1_2 weights were not re-laid-out");
+  Conv1FusedArgs fa{};
+  fa.x = x_nchw; fa.w1 = w1_oihw; fa.bias1 = bias1;
+  ConvTcArgs& a = fa.c2;
+  a.N = N; a.H = H; a.W = W; a.cin = 64; a.cout = 64;
+  a.tw_log2 = 3;
+  a.tiles_w = cdiv(W, 8);
+  a.tiles_h = cdiv(H, 16);
+  a.n_tiles = 1;
+  a.total_tiles = (int)((long long)N * a.tiles_h * a.tiles_w);
+  a.relu = 1; a.pool = 1;
+  a.bias = p2.bias; a.y_hi = y_hi; a.y_lo = y_lo; a.y_f32 = nullptr; a.ssq = nullptr; a.ssq_stride = 0;
+  CUtensorMap m_whi, m_wlo;
+  {
+    uint64_t dims[3] = {64, 64, 9};
+    uint64_t str[2] = {64 * 2, 64 * 64 * 2};
+    uint32_t box[3] = {64, 64, 1};
+    IBL_RET(make_tmap(&m_whi, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 3, p2.w_hi, dims, str, box));
+    IBL_RET(make_tmap(&m_wlo, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 3, p2.w_lo, dims, str, box));
+  }
+  static DeviceOnce attr_done;   // the attribute is per device
+  if (!attr_done.done()) {
+    IBL_CUDA_OK(cudaFuncSetAttribute(conv1_fused_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, F1_SMEM));
+    attr_done.mark();
+  }
+  const int sms = device_sm_count();
+  const int grid = a.total_tiles < sms ? a.total_tiles : sms;
+  conv1_fused_tc_kernel<<<grid, 448, F1_SMEM, s>>>(m_whi, m_wlo, fa);
+  IBL_CUDA_OK(cudaGetLastError());
+  return IBL_OK;
+}
+
 // ---- 2x2 max-pool on hi/lo planes (used only when the conv epilogue did not pool) -------------
 __global__ void maxpool2x2_planes_kernel(const __nv_bfloat16* __restrict__ hi,
                                          const __nv_bfloat16* __restrict__ lo, int N, int H, int W,
