@@ -109,30 +109,45 @@ __host__ __device__ constexpr uint32_t umma_idesc_f16_f32(int M, int N) {   // k
   return (1u << 4) | ((uint32_t)(N >> 3) << 17) | ((uint32_t)(M >> 4) << 24);
 }
 
-constexpr int D1_BN = 256, D1_BK = 64, D1_STAGES = 6;
+constexpr int D1_BN = 256, D1_BK = 64;
 constexpr int D1_A_BYTES = 128 * D1_BK * 2;            // 16 KiB: this CTA's 128 query rows
-constexpr int D1_BH_BYTES = (D1_BN / 2) * D1_BK * 2;   // 16 KiB: this CTA's half of the database tile
-constexpr int D1_STAGE = D1_A_BYTES + D1_BH_BYTES;     // 32 KiB
+constexpr int D1_BH_BYTES = (D1_BN / 2) * D1_BK * 2;   // 16 KiB: this CTA's half of one 256-row database sub-tile
 
+// SUB = 256-row database sub-tiles per work tile.  One fp16 pass needs 64 B/clk/SM of operands at 256 x 256 per SM
+// pair -- more than the L2 delivers (~43 B/clk/SM chip-wide) -- so the default is SUB = 2: a 256 x 512 tile reuses
+// every staged query block for two MMAs (48 KiB per stage instead of 2 x 32), with ONE 512-column accumulator: the
+// epilogue of a tile is not overlapped with the next main loop (~5 % of a K = 4096 tile).  SUB = 1 keeps two
+// 256-column accumulators and overlaps them.
+template <int SUB> struct D1Cfg {
+  static constexpr int STAGES = SUB == 1 ? 6 : 4;
+  static constexpr int STAGE = D1_A_BYTES + SUB * D1_BH_BYTES;
+  static constexpr int TILE_N = D1_BN * SUB;
+  static constexpr int ACC_BUFS = SUB == 1 ? 2 : 1;
+  static constexpr int SMEM = STAGES * STAGE + 1024 + 256;
+};
+
+template <int SUB>
 __global__ void __launch_bounds__(192, 1)
 gemm2_f16_top16_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constant__ CUtensorMap tm_b,
                        const Dist1Args g) {
+  using C = D1Cfg<SUB>;
+  constexpr int STAGES = C::STAGES, STAGE = C::STAGE, TILE_N = C::TILE_N;
   const uint32_t rank = cluster_ctarank();
   const bool leader = rank == 0;
   const int unit0 = blockIdx.x >> 1, unit_stride = gridDim.x >> 1;
   extern __shared__ __align__(1024) uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
-  uint64_t* bars = reinterpret_cast<uint64_t*>(smem + D1_STAGES * D1_STAGE);
-  uint64_t* full_bar = bars;                       // leader's are used: count 2 (leader expect_tx + peer arrive)
-  uint64_t* empty_bar = bars + D1_STAGES;          // local, count 1 (multicast commit)
-  uint64_t* tfull_bar = bars + 2 * D1_STAGES;      // local, count 1 (multicast commit)
-  uint64_t* tempty_bar = bars + 2 * D1_STAGES + 2; // leader's are used: count 8 (4 epilogue warps x 2 CTAs)
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 2 * D1_STAGES + 4);
+  uint64_t* bars = reinterpret_cast<uint64_t*>(smem + STAGES * STAGE);
+  uint64_t* full_bar = bars;                    // leader's are used: count 2 (leader expect_tx + peer arrive)
+  uint64_t* empty_bar = bars + STAGES;          // local, count 1 (multicast commit)
+  uint64_t* tfull_bar = bars + 2 * STAGES;      // local, count 1 (multicast commit)
+  uint64_t* tempty_bar = bars + 2 * STAGES + 2; // leader's are used: count 8 (4 epilogue warps x 2 CTAs)
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 2 * STAGES + 4);
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
 
   if (warp == 0 && lane == 0) {
     tma_prefetch_desc(&tm_a); tma_prefetch_desc(&tm_b);
-    for (int i = 0; i < D1_STAGES; ++i) { mbar_init(&full_bar[i], 2); mbar_init(&empty_bar[i], 1); }
+    for (int i = 0; i < STAGES; ++i) { mbar_init(&full_bar[i], 2); mbar_init(&empty_bar[i], 1); }
     mbar_init(&tfull_bar[0], 1); mbar_init(&tfull_bar[1], 1);
     mbar_init(&tempty_bar[0], 8); mbar_init(&tempty_bar[1], 8);
     fence_barrier_init();
@@ -161,16 +176,18 @@ gemm2_f16_top16_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_co
         decode(item, mp, nt0, ntn);
         const int row0 = (mp * 2 + (int)rank) * 128;
         for (int nt = nt0; nt < nt0 + ntn; ++nt) {
-          const int col0 = nt * D1_BN + (int)rank * (D1_BN / 2);
+          const int col0 = nt * TILE_N + (int)rank * (D1_BN / 2);
           for (int kit = 0; kit < kiters; ++kit) {
             mbar_wait(&empty_bar[stage], phase ^ 1);
-            uint8_t* st = smem + stage * D1_STAGE;
+            uint8_t* st = smem + stage * STAGE;
             const uint32_t lead_full = mapa_u32(smem_u32(&full_bar[stage]), 0);
-            if (leader) mbar_arrive_expect_tx(&full_bar[stage], 2 * D1_STAGE);   // bytes of BOTH CTAs
+            if (leader) mbar_arrive_expect_tx(&full_bar[stage], 2 * STAGE);   // bytes of BOTH CTAs
             else mbar_arrive_remote(lead_full);
             tma_load_2d_2sm(st, &tm_a, lead_full, kit * D1_BK, row0);
-            tma_load_2d_2sm(st + D1_A_BYTES, &tm_b, lead_full, kit * D1_BK, col0);
-            if (++stage == D1_STAGES) { stage = 0; phase ^= 1; }
+#pragma unroll
+            for (int j = 0; j < SUB; ++j)     // rows beyond the matrix are zero-filled by the TMA unit
+              tma_load_2d_2sm(st + D1_A_BYTES + j * D1_BH_BYTES, &tm_b, lead_full, kit * D1_BK, col0 + j * D1_BN);
+            if (++stage == STAGES) { stage = 0; phase ^= 1; }
           }
         }
       }
@@ -184,21 +201,27 @@ gemm2_f16_top16_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_co
         int mp, nt0, ntn;
         decode(item, mp, nt0, ntn);
         for (int nt = nt0; nt < nt0 + ntn; ++nt, ++it) {
-          const int as = it & 1;
-          const uint32_t aphase = (it >> 1) & 1;
+          const int as = C::ACC_BUFS == 2 ? (it & 1) : 0;
+          const uint32_t aphase = C::ACC_BUFS == 2 ? ((it >> 1) & 1) : (it & 1);
           mbar_wait(&tempty_bar[as], aphase ^ 1);
           tc_fence_after();
           const uint32_t d_tmem = tmem_base + as * D1_BN;
           for (int kit = 0; kit < kiters; ++kit) {
             mbar_wait(&full_bar[stage], phase);
             tc_fence_after();
-            const uint32_t sa = smem_u32(smem + stage * D1_STAGE);
-            const uint64_t a = umma_desc_kmajor_sw128(sa), b = umma_desc_kmajor_sw128(sa + D1_A_BYTES);
+            const uint32_t sa = smem_u32(smem + stage * STAGE);
+            const uint64_t a = umma_desc_kmajor_sw128(sa);
 #pragma unroll
-            for (int k = 0; k < D1_BK / 16; ++k)
-              umma_bf16_2sm(d_tmem, a + (uint64_t)(k * 2), b + (uint64_t)(k * 2), idesc, (kit > 0 || k > 0) ? 1u : 0u);
+            for (int k = 0; k < D1_BK / 16; ++k) {
+#pragma unroll
+              for (int j = 0; j < SUB; ++j) {
+                const uint64_t b = umma_desc_kmajor_sw128(sa + D1_A_BYTES + j * D1_BH_BYTES);
+                umma_bf16_2sm(d_tmem + j * D1_BN, a + (uint64_t)(k * 2), b + (uint64_t)(k * 2), idesc,
+                              (kit > 0 || k > 0) ? 1u : 0u);
+              }
+            }
             umma_commit_2sm_mc(&empty_bar[stage], 0x3);
-            if (++stage == D1_STAGES) { stage = 0; phase ^= 1; }
+            if (++stage == STAGES) { stage = 0; phase ^= 1; }
           }
           umma_commit_2sm_mc(&tfull_bar[as], 0x3);
         }
@@ -220,17 +243,18 @@ gemm2_f16_top16_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_co
 #pragma unroll
       for (int j = 0; j < 16; ++j) { td[j] = INFINITY; ti[j] = -1; }
       for (int nt = nt0; nt < nt0 + ntn; ++nt, ++it) {
-        const int as = it & 1;
-        const uint32_t aphase = (it >> 1) & 1;
+        const int as = C::ACC_BUFS == 2 ? (it & 1) : 0;
+        const uint32_t aphase = C::ACC_BUFS == 2 ? ((it >> 1) & 1) : (it & 1);
         mbar_wait(&tfull_bar[as], aphase);
         tc_fence_after();
         const uint32_t t_row = tmem_base + ((uint32_t)(q * 32) << 16) + as * D1_BN;
 #pragma unroll 1
-        for (int ch = 0; ch < D1_BN / 32; ++ch) {
+        for (int ch = 0; ch < TILE_N / 32; ++ch) {
+          const int col0 = nt * TILE_N + ch * 32;
+          if (col0 >= g.n_valid) break;                    // warp-uniform: the rest of the tile is padding
           uint32_t raw[32];
           tmem_ld_32x32(t_row + ch * 32, raw);
           tmem_ld_wait();
-          const int col0 = nt * D1_BN + ch * 32;
 #pragma unroll
           for (int j = 0; j < 32; ++j) {
             const int col = col0 + j;
@@ -576,9 +600,12 @@ int launch_dist_topk_1pass(const float* q, int m, const float* db, int n, int n_
     IBL_RET(make_tmap(&ma, CU_TENSOR_MAP_DATA_TYPE_FLOAT16, 2, qp, dims_a, str, box));
     IBL_RET(make_tmap(&mb, CU_TENSOR_MAP_DATA_TYPE_FLOAT16, 2, dp, dims_b, str, box));
   }
+  // IBL_DIST_BN=256 selects the 256 x 256 tile with two overlapped accumulators (A/B measurements, variant tests)
+  static const int tile_env = [] { const char* v = getenv("IBL_DIST_BN"); return v ? atoi(v) : 512; }();
+  const int SUBn = tile_env == 256 ? 1 : 2;
   Dist1Args g{};
   g.M = m; g.N = n; g.K = d;
-  g.n_tiles = cdiv(n_valid, D1_BN);
+  g.n_tiles = cdiv(n_valid, D1_BN * SUBn);
   const int m_pairs = cdiv(cdiv(m, 128), 2);
   const int runs = pick_runs1(m_pairs, g.n_tiles);
   g.nt_per_item = cdiv(g.n_tiles, runs);
@@ -586,10 +613,10 @@ int launch_dist_topk_1pass(const float* q, int m, const float* db, int n, int n_
   g.total_items = m_pairs * g.items_per_mpair;
   g.n_valid = n_valid;
   g.a_aux = qa; g.b_aux = da; g.cand_d = cd; g.cand_i = ci;
-  const int smem = D1_STAGES * D1_STAGE + 1024 + 256;
   static DeviceOnce attr_done;   // the attributes are per device
   if (!attr_done.done()) {
-    IBL_CUDA_OK(cudaFuncSetAttribute(gemm2_f16_top16_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
+    IBL_CUDA_OK(cudaFuncSetAttribute(gemm2_f16_top16_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, D1Cfg<1>::SMEM));
+    IBL_CUDA_OK(cudaFuncSetAttribute(gemm2_f16_top16_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, D1Cfg<2>::SMEM));
     IBL_CUDA_OK(cudaFuncSetAttribute(dist_finish_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 64 * 1024));
     IBL_CUDA_OK(cudaFuncSetAttribute(dist_exact_chunk_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 64 * 1024));
     attr_done.mark();
@@ -599,7 +626,7 @@ int launch_dist_topk_1pass(const float* q, int m, const float* db, int n, int n_
   cudaLaunchConfig_t cfg{};
   cfg.gridDim = dim3(2 * units);
   cfg.blockDim = dim3(192);
-  cfg.dynamicSmemBytes = smem;
+  cfg.dynamicSmemBytes = SUBn == 1 ? D1Cfg<1>::SMEM : D1Cfg<2>::SMEM;
   cfg.stream = s;
   cudaLaunchAttribute attr[1];
   attr[0].id = cudaLaunchAttributeClusterDimension;
@@ -608,7 +635,8 @@ int launch_dist_topk_1pass(const float* q, int m, const float* db, int n, int n_
   attr[0].val.clusterDim.z = 1;
   cfg.attrs = attr;
   cfg.numAttrs = 1;
-  IBL_CUDA_OK(cudaLaunchKernelEx(&cfg, gemm2_f16_top16_kernel, ma, mb, g));
+  if (SUBn == 1) IBL_CUDA_OK(cudaLaunchKernelEx(&cfg, gemm2_f16_top16_kernel<1>, ma, mb, g));
+  else IBL_CUDA_OK(cudaLaunchKernelEx(&cfg, gemm2_f16_top16_kernel<2>, ma, mb, g));
 
   FinishArgs f{};
   f.q = q; f.db = db; f.q_aux = qa; f.db_aux = da; f.db_max2 = dmax2; f.cand_d = cd; f.cand_i = ci;
