@@ -88,7 +88,21 @@ struct ConvTcArgs {
   float* y_f32;
   float* ssq;             // optional [n_tiles][N*H*W] per-pixel sum of squares of the outputs (no pool)
   long long ssq_stride;
+  float acc_scale;        // compensation of the tcgen05 accumulator's round-toward-zero bias (see tc_acc_scale)
 };
+
+// The tcgen05 fp32 accumulator truncates toward zero: every accumulating MMA loses on average 2^-26 of the running
+// sum (measured per layer shape, profiles/r01_diag_tc_accumulator_bias.txt: -1.31e-8 .. -1.38e-8 per MMA with ReLU'd
+// inputs, linear in the number of MMAs from 108 to 864).  Over the 12 layers that is one uniform factor (1 - 9e-5) on
+// the conv5_3 map -- harmless after the L2 normalisations, but it put VGG.forward's own output outside the 1e-4
+// tolerance.  The epilogue multiplies the accumulator by 1 + n_mma * 1.32e-8 (n_mma = MMAs accumulated into the
+// dominant accumulator block) before the bias is added.  IBL_TC_BIAS_COMP=0 switches it off (diagnosis).
+static float tc_acc_scale(int cin, bool concat) {
+  static const bool on = [] { const char* v = getenv("IBL_TC_BIAS_COMP"); return !v || atoi(v) != 0; }();
+  if (!on) return 1.f;
+  const int n_mma = (concat ? 9 : 27) * (cin / 16);
+  return 1.f + (float)n_mma * 1.32e-8f;
+}
 
 constexpr int TC_BM = 128;
 constexpr int TC_BK = 64;                       // bf16 elements per K-chunk = one 128-byte row
@@ -157,10 +171,10 @@ __device__ __forceinline__ void conv_epilogue_tile(const ConvTcArgs& a, uint32_t
 #pragma unroll
     for (int j = 0; j < 8; ++j) {
       const float4 b = __ldg(bp + j);
-      v[4 * j + 0] = __uint_as_float(raw[4 * j + 0]) + b.x;
-      v[4 * j + 1] = __uint_as_float(raw[4 * j + 1]) + b.y;
-      v[4 * j + 2] = __uint_as_float(raw[4 * j + 2]) + b.z;
-      v[4 * j + 3] = __uint_as_float(raw[4 * j + 3]) + b.w;
+      v[4 * j + 0] = fmaf(__uint_as_float(raw[4 * j + 0]), a.acc_scale, b.x);
+      v[4 * j + 1] = fmaf(__uint_as_float(raw[4 * j + 1]), a.acc_scale, b.y);
+      v[4 * j + 2] = fmaf(__uint_as_float(raw[4 * j + 2]), a.acc_scale, b.z);
+      v[4 * j + 3] = fmaf(__uint_as_float(raw[4 * j + 3]), a.acc_scale, b.w);
     }
     if (a.relu) {
 #pragma unroll
@@ -619,6 +633,7 @@ int launch_conv3x3_tc(const __nv_bfloat16* x_hi, const __nv_bfloat16* x_lo, cons
   a.bias = p.bias; a.y_hi = y_hi; a.y_lo = y_lo; a.y_f32 = y_f32;
   a.ssq = pool ? nullptr : ssq;
   a.ssq_stride = (long long)N * H * W;
+  a.acc_scale = tc_acc_scale(cin, bn == 64);
   if (ssq_parts) *ssq_parts = a.n_tiles;
 
   CUtensorMap m_xhi, m_xlo, m_whi, m_wlo;
@@ -993,6 +1008,7 @@ int launch_conv1_fused_tc(const float* x_nchw, const float* w1_oihw, const float
   a.total_tiles = (int)((long long)N * a.tiles_h * a.tiles_w);
   a.relu = 1; a.pool = 1;
   a.bias = p2.bias; a.y_hi = y_hi; a.y_lo = y_lo; a.y_f32 = nullptr; a.ssq = nullptr; a.ssq_stride = 0;
+  a.acc_scale = tc_acc_scale(64, true);
   CUtensorMap m_whi, m_wlo;
   {
     uint64_t dims[3] = {64, 64, 9};
