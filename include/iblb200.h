@@ -153,6 +153,14 @@ int ibl_extract(ibl_engine* e, const float* x_nchw, int N, int H, int W, unsigne
 int ibl_extract_host(ibl_engine* e, const float* x_nchw_host, int N, int H, int W,
                      unsigned flags, float* out_host, float* pool_host, void* stream);
 
+/* Two-deep pipelined form of ibl_extract_host (the overlap a loader loop gets in the reference from pin_memory +
+ * non_blocking .cuda(), evaluators.py:24, here inside the library): submit(slot) enqueues H2D on the engine's copy
+ * stream, the extraction and the D2H of the descriptors, and returns without synchronising; wait(slot) blocks until
+ * that batch's descriptors are in out_host.  slot is 0 or 1; the host buffers must stay valid until wait returns. */
+int ibl_extract_host_submit(ibl_engine* e, int slot, const float* x_nchw_host, int N, int H, int W, unsigned flags,
+                            float* out_host, float* pool_host, void* stream);
+int ibl_extract_host_wait(ibl_engine* e, int slot);
+
 /* ---- input side: ToTensor + Normalize on the GPU ----------------------------- */
 /* The reference's test transform after the resize (ibl/utils/data/__init__.py:37-42: T.ToTensor(),
  * T.Normalize(mean, std)) applied to decoded uint8 HWC pixels: out[n,c,h,w] = ((x[n,h,w,c]/255) - mean[c]) / std[c],

@@ -45,6 +45,8 @@ SIGNATURES = {
     "ibl_l2_normalize_rows": (c_int, [_P, _P, c_int, c_int, _P, _P]),
     "ibl_extract": (c_int, [_P, _P, c_int, c_int, c_int, c_uint, _P, _P, _P]),
     "ibl_extract_host": (c_int, [_P, _P, c_int, c_int, c_int, c_uint, _P, _P, _P]),
+    "ibl_extract_host_submit": (c_int, [_P, c_int, _P, c_int, c_int, c_int, c_uint, _P, _P, _P]),
+    "ibl_extract_host_wait": (c_int, [_P, c_int]),
     "ibl_preprocess_u8": (c_int, [_P, _P, c_int, c_int, c_int, _P, _P, _P, _P]),
     "ibl_resize_bilinear_u8": (c_int, [_P, _P, c_int, c_int, c_int, c_int, c_int, _P, _P, c_int, _P, _P, c_int, _P, _P]),
     "ibl_extract_host_u8": (c_int, [_P, _P, c_int, c_int, c_int, _P, _P, c_uint, _P, _P, _P]),

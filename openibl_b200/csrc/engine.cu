@@ -87,6 +87,11 @@ struct ibl_engine {
   const float* nvw_pl_src = nullptr;
   cudaStream_t copy_stream = nullptr;   // H2D staging of ibl_extract_host overlaps compute
   cudaEvent_t copy_ev[2] = {nullptr, nullptr};
+  // two-deep pipelined host entry point (ibl_extract_host_submit / _wait): per slot an input staging buffer, an
+  // output staging buffer, "H2D done" and "slot done" events
+  DevBuf pipe_in[2], pipe_out[2], pipe_pool[2];
+  cudaEvent_t pipe_h2d[2] = {nullptr, nullptr}, pipe_done[2] = {nullptr, nullptr};
+  bool pipe_busy[2] = {false, false};
 };
 
 // conv5_3 output as bf16 hi/lo planes (fused-NetVLAD path)
@@ -260,6 +265,11 @@ int ibl_engine_destroy(ibl_engine* e) {
   }
   if (e->w0_oihw) cudaFree(e->w0_oihw);
   if (e->copy_stream) { cudaStreamDestroy(e->copy_stream); cudaEventDestroy(e->copy_ev[0]); cudaEventDestroy(e->copy_ev[1]); }
+  for (int i = 0; i < 2; ++i) {
+    if (e->pipe_h2d[i]) cudaEventDestroy(e->pipe_h2d[i]);
+    if (e->pipe_done[i]) cudaEventDestroy(e->pipe_done[i]);
+    e->pipe_in[i].release(); e->pipe_out[i].release(); e->pipe_pool[i].release();
+  }
   DevBuf* bufs[] = {&e->act[0], &e->act[1], &e->feat, &e->nv_assign, &e->nv_inv, &e->nv_raw, &e->vlad,
                     &e->pca_partial, &e->qn, &e->dbn, &e->dist_chunk, &e->cand_d, &e->cand_i,
                     &e->stage_in, &e->stage_out, &e->stage_out2, &e->stage_u8, &e->q_pl, &e->db_pl, &e->v_pl, &e->pca_pl,
@@ -701,6 +711,61 @@ int ibl_extract_host(ibl_engine* e, const float* x_host, int N, int H, int W, un
     IBL_CUDA_OK(cudaMemcpyAsync(pool_host, e->stage_out2.p, (size_t)N * 512 * sizeof(float),
                                 cudaMemcpyDeviceToHost, S(stream)));
   IBL_CUDA_OK(cudaStreamSynchronize(S(stream)));
+  return IBL_OK;
+}
+
+// Pipelined host entry point: what a loader loop overlaps by hand in the reference (pin_memory + non_blocking .cuda(),
+// evaluators.py:24) -- submit(slot) enqueues H2D of this batch on the engine's copy stream, the extraction behind it
+// on the caller's stream and the D2H of the descriptors, and returns WITHOUT synchronising; wait(slot) blocks until
+// that batch's descriptors are in out_host.  With two slots the copy of batch i+1 runs under the compute of batch i.
+// x_host / out_host (/ pool_host) must stay valid (and should be pinned) until wait(slot) returns.
+int ibl_extract_host_submit(ibl_engine* e, int slot, const float* x_host, int N, int H, int W, unsigned flags,
+                            float* out_host, float* pool_host, void* stream) {
+  IBL_REQUIRE(e && x_host && out_host, "null argument");
+  IBL_REQUIRE(slot == 0 || slot == 1, "slot must be 0 or 1");
+  IBL_REQUIRE(N >= 1 && H >= 16 && W >= 16, "VGG16 trunk needs N>=1 and H,W>=16");
+  IBL_REQUIRE(!e->pipe_busy[slot], "slot is in flight: call ibl_extract_host_wait first");
+  DeviceGuard g(e->device);
+  const bool pca = (flags & IBL_OUT_PCA) != 0;
+  const int out_dim = pca ? e->pca_P : e->nv_K * e->nv_C;
+  const size_t in_bytes = (size_t)N * 3 * H * W * sizeof(float), out_bytes = (size_t)N * out_dim * sizeof(float);
+  if (!e->copy_stream) {
+    IBL_CUDA_OK(cudaStreamCreateWithFlags(&e->copy_stream, cudaStreamNonBlocking));
+    IBL_CUDA_OK(cudaEventCreateWithFlags(&e->copy_ev[0], cudaEventDisableTiming));
+    IBL_CUDA_OK(cudaEventCreateWithFlags(&e->copy_ev[1], cudaEventDisableTiming));
+  }
+  if (!e->pipe_h2d[slot]) {
+    IBL_CUDA_OK(cudaEventCreateWithFlags(&e->pipe_h2d[slot], cudaEventDisableTiming));
+    IBL_CUDA_OK(cudaEventCreateWithFlags(&e->pipe_done[slot], cudaEventDisableTiming));
+  }
+  // growing a buffer frees the old one: make sure nothing of an earlier use of this slot is still running
+  if (e->pipe_in[slot].cap < in_bytes || e->pipe_out[slot].cap < out_bytes) IBL_CUDA_OK(cudaEventSynchronize(e->pipe_done[slot]));
+  IBL_RET(e->pipe_in[slot].ensure(in_bytes));
+  IBL_RET(e->pipe_out[slot].ensure(out_bytes));
+  if (flags & IBL_OUT_POOL) IBL_RET(e->pipe_pool[slot].ensure((size_t)N * 512 * sizeof(float)));
+  // the copy stream may overwrite this slot's input buffer only after the slot's previous extraction has read it
+  IBL_CUDA_OK(cudaStreamWaitEvent(e->copy_stream, e->pipe_done[slot], 0));
+  IBL_CUDA_OK(cudaMemcpyAsync(e->pipe_in[slot].p, x_host, in_bytes, cudaMemcpyHostToDevice, e->copy_stream));
+  IBL_CUDA_OK(cudaEventRecord(e->pipe_h2d[slot], e->copy_stream));
+  IBL_CUDA_OK(cudaStreamWaitEvent(S(stream), e->pipe_h2d[slot], 0));
+  IBL_RET(ibl_extract(e, e->pipe_in[slot].as<float>(), N, H, W, flags, e->pipe_out[slot].as<float>(),
+                      (flags & IBL_OUT_POOL) ? e->pipe_pool[slot].as<float>() : nullptr, stream));
+  IBL_CUDA_OK(cudaMemcpyAsync(out_host, e->pipe_out[slot].p, out_bytes, cudaMemcpyDeviceToHost, S(stream)));
+  if ((flags & IBL_OUT_POOL) && pool_host)
+    IBL_CUDA_OK(cudaMemcpyAsync(pool_host, e->pipe_pool[slot].p, (size_t)N * 512 * sizeof(float), cudaMemcpyDeviceToHost,
+                                S(stream)));
+  IBL_CUDA_OK(cudaEventRecord(e->pipe_done[slot], S(stream)));
+  e->pipe_busy[slot] = true;
+  return IBL_OK;
+}
+
+int ibl_extract_host_wait(ibl_engine* e, int slot) {
+  IBL_REQUIRE(e, "null engine");
+  IBL_REQUIRE(slot == 0 || slot == 1, "slot must be 0 or 1");
+  if (!e->pipe_busy[slot]) return IBL_OK;
+  DeviceGuard g(e->device);
+  IBL_CUDA_OK(cudaEventSynchronize(e->pipe_done[slot]));
+  e->pipe_busy[slot] = false;
   return IBL_OK;
 }
 

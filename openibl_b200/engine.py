@@ -250,6 +250,38 @@ class Engine:
                                         _stream(self.device)), "ibl_extract_host")
         return out_host
 
+    def extract_host_submit(self, slot: int, x_host: torch.Tensor, out_host: torch.Tensor, pca=False,
+                            pool_host: Optional[torch.Tensor] = None) -> None:
+        """Pipelined form of extract_host: enqueue H2D (copy stream), extraction and D2H for `slot` (0 or 1) and return
+        without synchronising; `extract_host_wait(slot)` blocks until out_host holds the descriptors.  With two slots
+        the copy of batch i+1 overlaps the compute of batch i.  Host tensors should be pinned and must stay alive."""
+        assert not x_host.is_cuda and not out_host.is_cuda and x_host.is_contiguous() and out_host.is_contiguous()
+        assert x_host.dtype == torch.float32 and out_host.dtype == torch.float32
+        N, _, H, W = x_host.shape
+        flags = OUT_VLAD | (OUT_PCA if pca else 0) | (OUT_POOL if pool_host is not None else 0)
+        self._keep[("pipe", slot)] = (x_host, out_host, pool_host)
+        check(self.lib.ibl_extract_host_submit(self.h, int(slot), _ptr(x_host), N, H, W, flags, _ptr(out_host),
+                                               _ptr(pool_host), _stream(self.device)), "ibl_extract_host_submit")
+
+    def extract_host_wait(self, slot: int) -> None:
+        check(self.lib.ibl_extract_host_wait(self.h, int(slot)), "ibl_extract_host_wait")
+        self._keep.pop(("pipe", slot), None)
+
+    def extract_host_stream(self, batches, pca=False):
+        """Iterate (x_host, out_host) pairs through the two-slot pipeline; yields each out_host once it is complete."""
+        pending = []
+        for i, (x_host, out_host) in enumerate(batches):
+            slot = i & 1
+            if len(pending) == 2:
+                s0, o0 = pending.pop(0)
+                self.extract_host_wait(s0)
+                yield o0
+            self.extract_host_submit(slot, x_host, out_host, pca=pca)
+            pending.append((slot, out_host))
+        for s0, o0 in pending:
+            self.extract_host_wait(s0)
+            yield o0
+
     # ---- input side: ToTensor + Normalize on the device (utils/data/__init__.py:37-42) ------
     @staticmethod
     def _norm_consts(mean, std):

@@ -206,6 +206,14 @@ def test_shapes_tokyo_like_and_microbatching(eng, O):
     out_host2 = torch.empty(37, 256)                                        # pageable host memory also works
     eng.extract_host(x, out_host2, pca=True)
     assert torch.equal(out_host2, got.cpu())
+    # two-slot pipelined entry point: five batches in flight two at a time, same bits as the blocking call
+    xs = [synth.make_images(seed=60 + i, batch=3 + i, height=32, width=48).pin_memory() for i in range(5)]
+    outs = [torch.empty(3 + i, 256).pin_memory() for i in range(5)]
+    done = list(eng.extract_host_stream(zip(xs, outs), pca=True))
+    assert len(done) == 5
+    for xh, oh in zip(xs, outs):
+        want_i, _ = eng.extract(xh.cuda(), pca=True)
+        assert torch.equal(oh, want_i.cpu())
 
 
 def test_u8_preprocess_bit_exact_and_host_u8_path(eng):
