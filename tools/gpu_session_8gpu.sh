@@ -8,5 +8,5 @@ echo "gallery rc=$?"; grep '^{' gpurun_out/r02_gallery250k_8gpu.log | tail -1 > 
 timeout 300 $TR --master-port 29812 examples/sfrs_step_synthetic.py --launcher pytorch --tuple-size 4 --neg-num 10 --diff-num 10 \
     --height 480 --width 640 --steps 2 > gpurun_out/r02_sfrs_step_8gpu.log 2>&1
 echo "sfrs rc=$?"; grep SFRS_STEP gpurun_out/r02_sfrs_step_8gpu.log | tail -1
-timeout 600 python -m pytest tests/test_gpu_e2e_api.py -q -p no:cacheprovider > gpurun_out/r02_tests_8gpu.log 2>&1
+timeout 600 python -m pytest tests/test_gpu_e2e_api.py tests/test_gpu_dropin_reference_script.py -q -p no:cacheprovider > gpurun_out/r02_tests_8gpu.log 2>&1
 echo "pytest rc=$?"; tail -4 gpurun_out/r02_tests_8gpu.log
