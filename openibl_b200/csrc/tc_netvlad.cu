@@ -207,60 +207,77 @@ __device__ __forceinline__ void nv_finalize_image(const NvTcArgs& a, int b, int 
   }
   asm volatile("bar.sync 1, 128;" ::: "memory");
   float tot = 0.f;
-  // Latency-bound on one SM (640 KB from L2): every row iteration issues its 16 x G loads before the first add.
+  // Latency-bound on one SM (640 KB from L2): two rows per iteration, 16-byte loads, all 2 x 4 x (G + 1) loads of an
+  // iteration issued before the first add.  Lane L owns channels 4L .. 4L+3 of every 128-channel block.
 #pragma unroll 1
-  for (int r = 0; r < 16; ++r) {
-    const int k = q * 16 + r;
-    const float asum = sm[k];
-    float v[16], cz[16];
+  for (int r = 0; r < 16; r += 2) {
+    float4 v[2][4], cz[2][4];
 #pragma unroll
-    for (int j = 0; j < 16; ++j) { v[j] = 0.f; cz[j] = __ldg(a.cent + k * 512 + lane + 32 * j); }
+    for (int u = 0; u < 2; ++u)
+#pragma unroll
+      for (int j = 0; j < 4; ++j) {
+        v[u][j] = make_float4(0.f, 0.f, 0.f, 0.f);
+        cz[u][j] = __ldg(reinterpret_cast<const float4*>(a.cent + (q * 16 + r + u) * 512 + 4 * lane + 128 * j));
+      }
 #pragma unroll
     for (int g = 0; g < 4; ++g) {                      // G <= 4 (netvlad_tc_units); partials added in index order
       if (g < a.G) {
-        const float* pg = a.part + ((ub + g) * 64 + k) * 512 + lane;
-        float t[16];
+        float4 t[2][4];
 #pragma unroll
-        for (int j = 0; j < 16; ++j) t[j] = __ldcg(pg + 32 * j);
+        for (int u = 0; u < 2; ++u)
 #pragma unroll
-        for (int j = 0; j < 16; ++j) v[j] += t[j];
+          for (int j = 0; j < 4; ++j)
+            t[u][j] = __ldcg(reinterpret_cast<const float4*>(a.part + ((ub + g) * 64 + q * 16 + r + u) * 512 + 4 * lane + 128 * j));
+#pragma unroll
+        for (int u = 0; u < 2; ++u)
+#pragma unroll
+          for (int j = 0; j < 4; ++j) {
+            v[u][j].x += t[u][j].x; v[u][j].y += t[u][j].y; v[u][j].z += t[u][j].z; v[u][j].w += t[u][j].w;
+          }
       }
     }
-    float ss = 0.f;
 #pragma unroll
-    for (int j = 0; j < 16; ++j) {
-      v[j] -= cz[j] * asum;
-      ss = fmaf(v[j], v[j], ss);
+    for (int u = 0; u < 2; ++u) {
+      const int k = q * 16 + r + u;
+      const float asum = sm[k];
+      float ss = 0.f;
+#pragma unroll
+      for (int j = 0; j < 4; ++j) {
+        v[u][j].x -= cz[u][j].x * asum; v[u][j].y -= cz[u][j].y * asum;
+        v[u][j].z -= cz[u][j].z * asum; v[u][j].w -= cz[u][j].w * asum;
+        ss = fmaf(v[u][j].x, v[u][j].x, ss); ss = fmaf(v[u][j].y, v[u][j].y, ss);
+        ss = fmaf(v[u][j].z, v[u][j].z, ss); ss = fmaf(v[u][j].w, v[u][j].w, ss);
+      }
+#pragma unroll
+      for (int o = 16; o > 0; o >>= 1) ss += __shfl_xor_sync(0xffffffffu, ss, o);
+      const float inv = 1.f / fmaxf(sqrtf(ss), 1e-12f);
+      float s2 = 0.f;
+      const long long row = ((long long)b * 64 + k) * 512 + 4 * lane;
+#pragma unroll
+      for (int j = 0; j < 4; ++j) {
+        if (a.vlad_raw) *reinterpret_cast<float4*>(a.vlad_raw + row + 128 * j) = v[u][j];
+        const float4 w = make_float4(v[u][j].x * inv, v[u][j].y * inv, v[u][j].z * inv, v[u][j].w * inv);
+        s2 = fmaf(w.x, w.x, s2); s2 = fmaf(w.y, w.y, s2); s2 = fmaf(w.z, w.z, s2); s2 = fmaf(w.w, w.w, s2);
+        if (a.vlad_norm) *reinterpret_cast<float4*>(a.vlad_norm + row + 128 * j) = w;
+      }
+#pragma unroll
+      for (int o = 16; o > 0; o >>= 1) s2 += __shfl_xor_sync(0xffffffffu, s2, o);
+      tot += s2;
     }
-#pragma unroll
-    for (int o = 16; o > 0; o >>= 1) ss += __shfl_xor_sync(0xffffffffu, ss, o);
-    const float inv = 1.f / fmaxf(sqrtf(ss), 1e-12f);
-    float s2 = 0.f;
-    const long long row = ((long long)b * 64 + k) * 512;
-#pragma unroll
-    for (int j = 0; j < 16; ++j) {
-      const int c = lane + 32 * j;
-      if (a.vlad_raw) a.vlad_raw[row + c] = v[j];
-      const float w = v[j] * inv;
-      s2 = fmaf(w, w, s2);
-      if (a.vlad_norm) a.vlad_norm[row + c] = w;
-    }
-#pragma unroll
-    for (int o = 16; o > 0; o >>= 1) s2 += __shfl_xor_sync(0xffffffffu, s2, o);
-    tot += s2;
   }
   if (!a.vlad_norm) return;                          // block-uniform
   if (lane == 0) sm[128 + q] = tot;
   asm volatile("bar.sync 1, 128;" ::: "memory");
   const float ginv = 1.f / fmaxf(sqrtf((sm[128] + sm[129]) + (sm[130] + sm[131])), 1e-12f);
 #pragma unroll 1
-  for (int r4 = 0; r4 < 4; ++r4) {                   // 4 rows = 64 independent loads per thread in flight
-    float* o = a.vlad_norm + ((long long)b * 64 + q * 16 + r4 * 4) * 512 + lane;
-    float t[64];
+  for (int r8 = 0; r8 < 2; ++r8) {                   // 8 rows = 32 independent 16-byte loads per thread in flight
+    float4* o = reinterpret_cast<float4*>(a.vlad_norm + ((long long)b * 64 + q * 16 + r8 * 8) * 512 + 4 * lane);
+    float4 t[32];
 #pragma unroll
-    for (int i = 0; i < 64; ++i) t[i] = o[(i >> 4) * 512 + 32 * (i & 15)];
+    for (int i = 0; i < 32; ++i) t[i] = o[(i >> 2) * 128 + 32 * (i & 3)];
 #pragma unroll
-    for (int i = 0; i < 64; ++i) o[(i >> 4) * 512 + 32 * (i & 15)] = t[i] * ginv;
+    for (int i = 0; i < 32; ++i)
+      o[(i >> 2) * 128 + 32 * (i & 3)] = make_float4(t[i].x * ginv, t[i].y * ginv, t[i].z * ginv, t[i].w * ginv);
   }
 }
 
