@@ -263,11 +263,11 @@ conv3x3_tc_kernel(const __grid_constant__ CUtensorMap tm_xhi, const __grid_const
     tma_prefetch_desc(&tm_whi);
     tma_prefetch_desc(&tm_wlo);
     for (int i = 0; i < STAGES; ++i) {
-      mbar_init(&full_bar[i], PAIR ? 2 : 1);    // pair: leader's expect_tx + the peer producer's arrive
+      mbar_init(&full_bar[i], 1);    // pair: the leader's arrive.expect_tx covers both CTAs' bytes; the peer only loads (tc_dist1.cu)
       mbar_init(&empty_bar[i], 1);
     }
     for (int i = 0; i < NA; ++i) {
-      mbar_init(&afull_bar[i], PAIR ? 2 : 1);
+      mbar_init(&afull_bar[i], 1);
       mbar_init(&aempty_bar[i], 1);
     }
     mbar_init(&tfull_bar[0], 1);
@@ -327,7 +327,6 @@ conv3x3_tc_kernel(const __grid_constant__ CUtensorMap tm_xhi, const __grid_const
             if (PAIR) {
               const uint32_t lead = mapa_u32(smem_u32(&afull_bar[astage]), 0);
               if (leader) mbar_arrive_expect_tx(&afull_bar[astage], 2 * kHaloBytes);
-              else mbar_arrive_remote(lead);
               tma_load_4d_2sm(sa, &tm_xhi, lead, c0, w0 - 1, h0 - 1, img);
               tma_load_4d_2sm(sa + TC_HALO_PLANE, &tm_xlo, lead, c0, w0 - 1, h0 - 1, img);
             } else {
@@ -347,7 +346,6 @@ conv3x3_tc_kernel(const __grid_constant__ CUtensorMap tm_xhi, const __grid_const
             if (PAIR) {
               const uint32_t lead_full = mapa_u32(smem_u32(&full_bar[stage]), 0);
               if (leader) mbar_arrive_expect_tx(&full_bar[stage], 2 * STAGE_BYTES);
-              else mbar_arrive_remote(lead_full);
               tma_load_3d_2sm(st, &tm_whi, lead_full, c0, n0, tapB);
               tma_load_3d_2sm(st + B_BYTES, &tm_wlo, lead_full, c0, n0, tapB);
             } else {
@@ -378,7 +376,6 @@ conv3x3_tc_kernel(const __grid_constant__ CUtensorMap tm_xhi, const __grid_const
           if (PAIR) {
             const uint32_t lead_full = mapa_u32(smem_u32(&full_bar[stage]), 0);
             if (leader) mbar_arrive_expect_tx(&full_bar[stage], 2 * STAGE_BYTES);   // bytes of both CTAs
-            else mbar_arrive_remote(lead_full);
             tma_load_4d_2sm(st, &tm_xhi, lead_full, c0, w0 + kw, h0 + kh, img);
             tma_load_4d_2sm(st + TC_A_BYTES, &tm_xlo, lead_full, c0, w0 + kw, h0 + kh, img);
             tma_load_3d_2sm(st + 2 * TC_A_BYTES, &tm_whi, lead_full, c0, n0, tap);

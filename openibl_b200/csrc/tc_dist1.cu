@@ -126,6 +126,13 @@ template <int SUB> struct D1Cfg {
   static constexpr int SMEM = STAGES * STAGE + 1024 + 256;
 };
 
+// SM pairs: the peer CTA's producer does NOT arrive on the leader's full barrier.  The leader's single
+// arrive.expect_tx names the bytes of BOTH CTAs; the peer's TMA completions decrement the same transaction count
+// (complete_tx may land before the expect_tx: the phase still cannot complete before the leader's arrival).  Round 1
+// had the peer do an `mbarrier.arrive.release.cluster` per stage: that release fence waits for the peer's outstanding
+// bulk copies, which serialised its loads (~1 us per stage; ncu: 12 % tensor-pipe active on the single-pass distance
+// kernel, 13 % of L2 throughput).  The peer cannot lap the ring: it waits on its local empty barrier, which the
+// leader's multicast commit signals.
 template <int SUB>
 __global__ void __launch_bounds__(192, 1)
 gemm2_f16_top16_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constant__ CUtensorMap tm_b,
@@ -138,7 +145,7 @@ gemm2_f16_top16_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_co
   extern __shared__ __align__(1024) uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
   uint64_t* bars = reinterpret_cast<uint64_t*>(smem + STAGES * STAGE);
-  uint64_t* full_bar = bars;                    // leader's are used: count 2 (leader expect_tx + peer arrive)
+  uint64_t* full_bar = bars;                    // leader's are used: count 1 (the leader's arrive.expect_tx for both CTAs)
   uint64_t* empty_bar = bars + STAGES;          // local, count 1 (multicast commit)
   uint64_t* tfull_bar = bars + 2 * STAGES;      // local, count 1 (multicast commit)
   uint64_t* tempty_bar = bars + 2 * STAGES + 2; // leader's are used: count 8 (4 epilogue warps x 2 CTAs)
@@ -147,7 +154,7 @@ gemm2_f16_top16_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_co
 
   if (warp == 0 && lane == 0) {
     tma_prefetch_desc(&tm_a); tma_prefetch_desc(&tm_b);
-    for (int i = 0; i < STAGES; ++i) { mbar_init(&full_bar[i], 2); mbar_init(&empty_bar[i], 1); }
+    for (int i = 0; i < STAGES; ++i) { mbar_init(&full_bar[i], 1); mbar_init(&empty_bar[i], 1); }
     mbar_init(&tfull_bar[0], 1); mbar_init(&tfull_bar[1], 1);
     mbar_init(&tempty_bar[0], 8); mbar_init(&tempty_bar[1], 8);
     fence_barrier_init();
@@ -181,8 +188,7 @@ gemm2_f16_top16_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_co
             mbar_wait(&empty_bar[stage], phase ^ 1);
             uint8_t* st = smem + stage * STAGE;
             const uint32_t lead_full = mapa_u32(smem_u32(&full_bar[stage]), 0);
-            if (leader) mbar_arrive_expect_tx(&full_bar[stage], 2 * STAGE);   // bytes of BOTH CTAs
-            else mbar_arrive_remote(lead_full);
+            if (leader) mbar_arrive_expect_tx(&full_bar[stage], 2 * STAGE);   // bytes of BOTH CTAs; the peer only loads
             tma_load_2d_2sm(st, &tm_a, lead_full, kit * D1_BK, row0);
 #pragma unroll
             for (int j = 0; j < SUB; ++j)     // rows beyond the matrix are zero-filled by the TMA unit

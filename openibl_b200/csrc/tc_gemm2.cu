@@ -46,7 +46,7 @@ gemm2_top16_kernel(const __grid_constant__ CUtensorMap tm_ahi, const __grid_cons
   extern __shared__ __align__(1024) uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
   uint64_t* bars = reinterpret_cast<uint64_t*>(smem + G2_STAGES * G2_STAGE);
-  uint64_t* full_bar = bars;                       // leader's are used: count 2 (leader expect_tx + peer arrive)
+  uint64_t* full_bar = bars;                       // leader's are used: count 1 (leader's arrive.expect_tx for both CTAs; see tc_dist1.cu)
   uint64_t* empty_bar = bars + G2_STAGES;          // local, count 1 (multicast commit)
   uint64_t* tfull_bar = bars + 2 * G2_STAGES;      // local, count 1 (multicast commit)
   uint64_t* tempty_bar = bars + 2 * G2_STAGES + 2; // leader's are used: count 8 (4 epilogue warps x 2 CTAs)
@@ -55,7 +55,7 @@ gemm2_top16_kernel(const __grid_constant__ CUtensorMap tm_ahi, const __grid_cons
 
   if (warp == 0 && lane == 0) {
     tma_prefetch_desc(&tm_ahi); tma_prefetch_desc(&tm_alo); tma_prefetch_desc(&tm_bhi); tma_prefetch_desc(&tm_blo);
-    for (int i = 0; i < G2_STAGES; ++i) { mbar_init(&full_bar[i], 2); mbar_init(&empty_bar[i], 1); }
+    for (int i = 0; i < G2_STAGES; ++i) { mbar_init(&full_bar[i], 1); mbar_init(&empty_bar[i], 1); }
     mbar_init(&tfull_bar[0], 1); mbar_init(&tfull_bar[1], 1);
     mbar_init(&tempty_bar[0], 8); mbar_init(&tempty_bar[1], 8);
     fence_barrier_init();
@@ -91,8 +91,7 @@ gemm2_top16_kernel(const __grid_constant__ CUtensorMap tm_ahi, const __grid_cons
             mbar_wait(&empty_bar[stage], phase ^ 1);
             uint8_t* st = smem + stage * G2_STAGE;
             const uint32_t lead_full = mapa_u32(smem_u32(&full_bar[stage]), 0);
-            if (leader) mbar_arrive_expect_tx(&full_bar[stage], 2 * G2_STAGE);   // bytes of BOTH CTAs
-            else mbar_arrive_remote(lead_full);
+            if (leader) mbar_arrive_expect_tx(&full_bar[stage], 2 * G2_STAGE);   // bytes of BOTH CTAs; the peer only loads
             tma_load_2d_2sm(st, &tm_ahi, lead_full, kit * G2_BK, row0);
             tma_load_2d_2sm(st + G2_A_BYTES, &tm_alo, lead_full, kit * G2_BK, row0);
             tma_load_2d_2sm(st + 2 * G2_A_BYTES, &tm_bhi, lead_full, kit * G2_BK, col0);

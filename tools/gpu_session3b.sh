@@ -3,6 +3,13 @@
 # No ncu in this call.
 mkdir -p gpurun_out
 nvidia-smi --query-gpu=name,memory.used,memory.total --format=csv > gpurun_out/r02_gpu3b.txt; free -g >> gpurun_out/r02_gpu3b.txt
+# the SM-pair kernels changed their barrier protocol: check them first under a short timeout, stop the session if they fail
+timeout 300 python tools/check_pair_kernels.py > gpurun_out/r02_pair_check.log 2>&1; prc=$?
+tail -5 gpurun_out/r02_pair_check.log
+if [ $prc -ne 0 ]; then echo "PAIR KERNEL CHECK FAILED (rc=$prc) -> stopping"; exit 1; fi
+IBL_DIST_SCREEN=3 timeout 90 python tools/check_pair_kernels.py > gpurun_out/r02_pair_check3.log 2>&1; prc=$?
+tail -2 gpurun_out/r02_pair_check3.log
+if [ $prc -ne 0 ]; then echo "PAIR KERNEL CHECK (bf16x3 distance) FAILED (rc=$prc) -> stopping"; exit 1; fi
 timeout 100 python tools/check_fused_conv1.py gpurun_out/f1.pt --time > gpurun_out/r02_fused_on.log 2>&1; echo "fused-on rc=$?"
 nvidia-smi --query-gpu=name,memory.used --format=csv,noheader
 IBL_CONV1_FUSED=0 timeout 100 python tools/check_fused_conv1.py gpurun_out/f0.pt --time > gpurun_out/r02_fused_off.log 2>&1; echo "fused-off rc=$?"
