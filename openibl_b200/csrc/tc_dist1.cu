@@ -278,6 +278,11 @@ gemm2_f16_top16_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_co
         for (int ch = 0; ch < TILE_N / 32; ++ch) {
           const int col0 = nt * TILE_N + ch * 32;
           if (col0 >= g.n_valid) break;                    // warp-uniform: the rest of the tile is padding
+          if ((ch & 3) == 0 && ch > 0 && row_ok) {         // every 128 columns: publish, then refresh the shared gate
+            if (td[15] < cap) atomicMin(g.gate + row, d1_ord(td[15]));
+            const unsigned gv = *reinterpret_cast<volatile unsigned*>(g.gate + row);
+            if (gv != 0xFFFFFFFFu) cap = fminf(cap, d1_unord(gv));
+          }
           uint32_t raw[32];
           tmem_ld_32x32(t_row + ch * 32, raw);
           tmem_ld_wait();
@@ -290,15 +295,21 @@ gemm2_f16_top16_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_co
               d = fmaf(m2sa * t.y, __uint_as_float(raw[j]), an + t.x);
             }
             if (d < td[15] && d < cap) {
-              td[15] = d;
-              ti[15] = col;
+              // Sorted insert WITHOUT a dependency chain: the epilogue is one warp per scheduler, so a bubble of 15
+              // dependent compare-swaps ran at ~0.2 instructions per clock and made the epilogue (not the tensor pipe,
+              // not L2) the bound of the whole kernel (ncu: the MMA thread waiting on the accumulator-empty barrier).
+              // Here the slot is counted with 16 independent compares and every entry is rewritten from the OLD
+              // values of itself and its left neighbour (descending j), all independent of one another.
+              int pos = 0;
+#pragma unroll
+              for (int s = 0; s < 16; ++s) pos += (td[s] <= d) ? 1 : 0;
 #pragma unroll
               for (int s = 15; s > 0; --s) {
-                if (td[s] < td[s - 1]) {
-                  const float fd = td[s]; td[s] = td[s - 1]; td[s - 1] = fd;
-                  const int fi = ti[s]; ti[s] = ti[s - 1]; ti[s - 1] = fi;
-                }
+                const bool shift = s > pos, here = s == pos;
+                td[s] = shift ? td[s - 1] : (here ? d : td[s]);
+                ti[s] = shift ? ti[s - 1] : (here ? col : ti[s]);
               }
+              if (pos == 0) { td[0] = d; ti[0] = col; }
             }
           }
         }

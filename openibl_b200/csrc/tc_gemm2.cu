@@ -167,16 +167,17 @@ gemm2_top16_kernel(const __grid_constant__ CUtensorMap tm_ahi, const __grid_cons
             const int col = col0 + j;
             float d = INFINITY;
             if (col < g.n_valid) d = fmaf(-2.f, __uint_as_float(raw[j]), an + __ldg(g.bn + col));
-            if (d < td[15]) {
-              td[15] = d;
-              ti[15] = col;
+            if (d < td[15]) {       // chain-free sorted insert (see tc_dist1.cu)
+              int pos = 0;
+#pragma unroll
+              for (int s = 0; s < 16; ++s) pos += (td[s] <= d) ? 1 : 0;
 #pragma unroll
               for (int s = 15; s > 0; --s) {
-                if (td[s] < td[s - 1]) {
-                  const float fd = td[s]; td[s] = td[s - 1]; td[s - 1] = fd;
-                  const int fi = ti[s]; ti[s] = ti[s - 1]; ti[s - 1] = fi;
-                }
+                const bool shift = s > pos, here = s == pos;
+                td[s] = shift ? td[s - 1] : (here ? d : td[s]);
+                ti[s] = shift ? ti[s - 1] : (here ? col : ti[s]);
               }
+              if (pos == 0) { td[0] = d; ti[0] = col; }
             }
           }
         }
