@@ -283,23 +283,25 @@ gemm2_f16_top16_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_co
             const unsigned gv = *reinterpret_cast<volatile unsigned*>(g.gate + row);
             if (gv != 0xFFFFFFFFu) cap = fminf(cap, d1_unord(gv));
           }
+          // The per-column terms {|d|^2, 2^e} of this chunk: ONE coalesced load (lane j fetches column col0 + j) issued
+          // before the TMEM read, then broadcast by shuffles.  A `__ldg(b_aux + col)` per column, as round 1's kernels
+          // did, is a chain of 256 dependent L2-latency loads per tile and made the EPILOGUE the bound of every distance
+          // kernel (ncu source view: the stall samples sit on the first use of that load; the MMA thread waits on the
+          // accumulator-empty barrier).
+          float bx = INFINITY, by = 0.f;
+          if (col0 + lane < g.n_valid) { const float4 t = __ldg(g.b_aux + col0 + lane); bx = t.x; by = t.y; }
           uint32_t raw[32];
           tmem_ld_32x32(t_row + ch * 32, raw);
           tmem_ld_wait();
 #pragma unroll
           for (int j = 0; j < 32; ++j) {
             const int col = col0 + j;
-            float d = INFINITY;
-            if (col < g.n_valid) {
-              const float4 t = __ldg(g.b_aux + col);       // warp-uniform address: one broadcast load
-              d = fmaf(m2sa * t.y, __uint_as_float(raw[j]), an + t.x);
-            }
+            const float cx = __shfl_sync(0xffffffffu, bx, j), cy = __shfl_sync(0xffffffffu, by, j);
+            const float d = fmaf(m2sa * cy, __uint_as_float(raw[j]), an + cx);     // +inf for padding columns
             if (d < td[15] && d < cap) {
-              // Sorted insert WITHOUT a dependency chain: the epilogue is one warp per scheduler, so a bubble of 15
-              // dependent compare-swaps ran at ~0.2 instructions per clock and made the epilogue (not the tensor pipe,
-              // not L2) the bound of the whole kernel (ncu: the MMA thread waiting on the accumulator-empty barrier).
-              // Here the slot is counted with 16 independent compares and every entry is rewritten from the OLD
-              // values of itself and its left neighbour (descending j), all independent of one another.
+              // Sorted insert without a dependency chain (one warp per scheduler: a bubble of 15 dependent compare-swaps
+              // issues at a fraction of an instruction per clock): the slot is counted with 16 independent compares and
+              // every entry is rewritten from the OLD values of itself and its left neighbour (descending s).
               int pos = 0;
 #pragma unroll
               for (int s = 0; s < 16; ++s) pos += (td[s] <= d) ? 1 : 0;

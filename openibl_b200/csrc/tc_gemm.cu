@@ -242,21 +242,23 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tm_ahi, const __grid_constant
               }
             }
           } else {  // EPI_TOP16
+            // one coalesced load of the chunk's |d|^2 terms + shuffles, chain-free sorted insert (see tc_dist1.cu)
+            const float bmine = (col0 + (int)(threadIdx.x & 31) < g.n_valid) ? __ldg(g.bn + col0 + (threadIdx.x & 31)) : INFINITY;
 #pragma unroll
             for (int j = 0; j < 32; ++j) {
               const int col = col0 + j;
-              float d = INFINITY;
-              if (col < g.n_valid) d = fmaf(-2.f, __uint_as_float(raw[j]), an + __ldg(g.bn + col));
+              const float d = fmaf(-2.f, __uint_as_float(raw[j]), an + __shfl_sync(0xffffffffu, bmine, j));
               if (d < td[15]) {
-                td[15] = d;
-                ti[15] = col;
+                int pos = 0;
+#pragma unroll
+                for (int s = 0; s < 16; ++s) pos += (td[s] <= d) ? 1 : 0;
 #pragma unroll
                 for (int s = 15; s > 0; --s) {
-                  if (td[s] < td[s - 1]) {
-                    const float fd = td[s]; td[s] = td[s - 1]; td[s - 1] = fd;
-                    const int fi = ti[s]; ti[s] = ti[s - 1]; ti[s - 1] = fi;
-                  }
+                  const bool shift = s > pos, here = s == pos;
+                  td[s] = shift ? td[s - 1] : (here ? d : td[s]);
+                  ti[s] = shift ? ti[s - 1] : (here ? col : ti[s]);
                 }
+                if (pos == 0) { td[0] = d; ti[0] = col; }
               }
             }
           }

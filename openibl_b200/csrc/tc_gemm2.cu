@@ -158,15 +158,16 @@ gemm2_top16_kernel(const __grid_constant__ CUtensorMap tm_ahi, const __grid_cons
         const uint32_t t_row = tmem_base + ((uint32_t)(q * 32) << 16) + as * G2_BN;
 #pragma unroll 1
         for (int ch = 0; ch < G2_BN / 32; ++ch) {
+          const int col0 = nt * G2_BN + ch * 32;
+          // one coalesced load of the chunk's |d|^2 terms + shuffles instead of 32 dependent loads (see tc_dist1.cu)
+          const float bmine = (col0 + lane < g.n_valid) ? __ldg(g.bn + col0 + lane) : INFINITY;
           uint32_t raw[32];
           tmem_ld_32x32(t_row + ch * 32, raw);
           tmem_ld_wait();
-          const int col0 = nt * G2_BN + ch * 32;
 #pragma unroll
           for (int j = 0; j < 32; ++j) {
             const int col = col0 + j;
-            float d = INFINITY;
-            if (col < g.n_valid) d = fmaf(-2.f, __uint_as_float(raw[j]), an + __ldg(g.bn + col));
+            const float d = fmaf(-2.f, __uint_as_float(raw[j]), an + __shfl_sync(0xffffffffu, bmine, j));
             if (d < td[15]) {       // chain-free sorted insert (see tc_dist1.cu)
               int pos = 0;
 #pragma unroll
