@@ -118,7 +118,17 @@ __device__ __forceinline__ float d1_unord(uint32_t u) {
   return __uint_as_float((u & 0x80000000u) ? (u & 0x7fffffffu) : ~u);
 }
 
+__device__ __forceinline__ void d1_sts64(uint32_t addr, float x, float y) {
+  asm volatile("st.shared.v2.f32 [%0], {%1, %2};" ::"r"(addr), "f"(x), "f"(y) : "memory");
+}
+__device__ __forceinline__ float2 d1_lds64(uint32_t addr) {
+  float2 v;
+  asm volatile("ld.shared.v2.f32 {%0, %1}, [%2];" : "=f"(v.x), "=f"(v.y) : "r"(addr) : "memory");
+  return v;
+}
+
 constexpr int D1_BN = 256, D1_BK = 64;
+constexpr int D1_PEND = 32;                            // pending candidates per row between two merges (see the epilogue)
 constexpr int D1_A_BYTES = 128 * D1_BK * 2;            // 16 KiB: this CTA's 128 query rows
 constexpr int D1_BH_BYTES = (D1_BN / 2) * D1_BK * 2;   // 16 KiB: this CTA's half of one 256-row database sub-tile
 
@@ -132,7 +142,10 @@ template <int SUB> struct D1Cfg {
   static constexpr int STAGE = D1_A_BYTES + SUB * D1_BH_BYTES;
   static constexpr int TILE_N = D1_BN * SUB;
   static constexpr int ACC_BUFS = SUB == 1 ? 2 : 1;
-  static constexpr int SMEM = STAGES * STAGE + 1024 + 256;
+  static constexpr int BARS = 256;                      // mbarriers + the TMEM slot
+  static constexpr int BSTAGE = 4 * 32 * 8;             // per epilogue warp: {|d|^2, 2^e} of the 32 columns of a chunk
+  static constexpr int PEND = 128 * D1_PEND * 8;        // per query row: D1_PEND pending (distance, column) pairs
+  static constexpr int SMEM = STAGES * STAGE + BARS + BSTAGE + PEND + 1024;
 };
 
 // SM pairs: the peer CTA's producer does NOT arrive on the leader's full barrier.  The leader's single
@@ -243,8 +256,20 @@ gemm2_f16_top16_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_co
       }
     }
   } else {
+    // Epilogue: one warp per scheduler, one thread per query row, 256+ accumulator columns per tile.  With a single
+    // warp per scheduler every instruction counts (no other warp hides a dependent issue), and ncu's source view of the
+    // first version -- a sorted 16-entry insertion behind `if (d < td[15])` for every column -- showed ~85 executed
+    // warp instructions per column: whenever ANY of the 32 rows of the warp inserts (half of all columns at 10 k
+    // database rows per query) the whole warp walks the ~110-instruction insertion.  Here the per-column work is
+    // scale + compare + a predicated 8-byte shared-memory append to a per-row pending list; the lists are merged into
+    // the sorted top-16 in a compact loop (trip count = the longest list of the warp) when one could overflow within
+    // the next 16 columns, and at the end of every tile.  All 32 rows insert side by side in that loop, so the walk runs
+    // once per ~16 appended candidates of the fullest row instead of once per column with a candidate anywhere.
     const int q = warp & 3;
     const int rloc = q * 32 + lane;
+    // shared-state-space addresses (the generic pointer arithmetic above makes the compiler emit generic LD/ST)
+    const uint32_t bst = smem_u32(smem + STAGES * STAGE + C::BARS) + q * 256;
+    const uint32_t pend = smem_u32(smem + STAGES * STAGE + C::BARS + C::BSTAGE) + rloc * 8;   // [slot][128 rows] x 8 B
     int it = 0;
     for (int item = unit0; item < g.total_items; item += unit_stride) {
       int mp, nt0, ntn;
@@ -257,51 +282,21 @@ gemm2_f16_top16_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_co
       int ti[16];
 #pragma unroll
       for (int j = 0; j < 16; ++j) { td[j] = INFINITY; ti[j] = -1; }
-      for (int nt = nt0; nt < nt0 + ntn; ++nt, ++it) {
-        const int as = C::ACC_BUFS == 2 ? (it & 1) : 0;
-        const uint32_t aphase = C::ACC_BUFS == 2 ? ((it >> 1) & 1) : (it & 1);
-        // Shared gate: the work items of one query block scan different database ranges concurrently, each keeping its
-        // own top-16.  An element that is not below the 16th-best distance ANY of them has already reached cannot be in
-        // the merged top-16, so every item publishes its 16th-best (atomicMin) after each tile and reads the common
-        // value before the next: the gate tightens with the UNION of the columns scanned so far, and the warp-divergent
-        // insertion path (15 compare-swaps whenever any of the 32 lanes inserts) runs ~4x less often.  A stale read only
-        // costs efficiency.  Ties at the gate are dropped: the guard's error bound covers them.
-        float cap = INFINITY;
-        if (row_ok) {
-          const unsigned gv = *reinterpret_cast<volatile unsigned*>(g.gate + row);
-          if (gv != 0xFFFFFFFFu) cap = d1_unord(gv);       // 0xFFFFFFFF = "no gate yet" (the memset pattern)
-        }
-        mbar_wait(&tfull_bar[as], aphase);
-        tc_fence_after();
-        const uint32_t t_row = tmem_base + ((uint32_t)(q * 32) << 16) + as * D1_BN;
+      uint32_t paddr = pend;                               // next free slot of this row's pending list
+      float thr = row_ok ? INFINITY : -INFINITY;           // rows beyond the matrix never append
+      // merge this row's pending list into the sorted top-16; the 32 rows of the warp run the loop together
+      auto merge_pending = [&]() {
+        const int cnt = (int)((paddr - pend) >> 10);
+        const int longest = __reduce_max_sync(0xffffffffu, cnt);
 #pragma unroll 1
-        for (int ch = 0; ch < TILE_N / 32; ++ch) {
-          const int col0 = nt * TILE_N + ch * 32;
-          if (col0 >= g.n_valid) break;                    // warp-uniform: the rest of the tile is padding
-          if ((ch & 3) == 0 && ch > 0 && row_ok) {         // every 128 columns: publish, then refresh the shared gate
-            if (td[15] < cap) atomicMin(g.gate + row, d1_ord(td[15]));
-            const unsigned gv = *reinterpret_cast<volatile unsigned*>(g.gate + row);
-            if (gv != 0xFFFFFFFFu) cap = fminf(cap, d1_unord(gv));
-          }
-          // The per-column terms {|d|^2, 2^e} of this chunk: ONE coalesced load (lane j fetches column col0 + j) issued
-          // before the TMEM read, then broadcast by shuffles.  A `__ldg(b_aux + col)` per column, as round 1's kernels
-          // did, is a chain of 256 dependent L2-latency loads per tile and made the EPILOGUE the bound of every distance
-          // kernel (ncu source view: the stall samples sit on the first use of that load; the MMA thread waits on the
-          // accumulator-empty barrier).
-          float bx = INFINITY, by = 0.f;
-          if (col0 + lane < g.n_valid) { const float4 t = __ldg(g.b_aux + col0 + lane); bx = t.x; by = t.y; }
-          uint32_t raw[32];
-          tmem_ld_32x32(t_row + ch * 32, raw);
-          tmem_ld_wait();
-#pragma unroll
-          for (int j = 0; j < 32; ++j) {
-            const int col = col0 + j;
-            const float cx = __shfl_sync(0xffffffffu, bx, j), cy = __shfl_sync(0xffffffffu, by, j);
-            const float d = fmaf(m2sa * cy, __uint_as_float(raw[j]), an + cx);     // +inf for padding columns
-            if (d < td[15] && d < cap) {
-              // Sorted insert without a dependency chain (one warp per scheduler: a bubble of 15 dependent compare-swaps
-              // issues at a fraction of an instruction per clock): the slot is counted with 16 independent compares and
-              // every entry is rewritten from the OLD values of itself and its left neighbour (descending s).
+        for (int e = 0; e < longest; ++e) {
+          if (e < cnt) {
+            const float2 v = d1_lds64(pend + e * 1024);
+            const float d = v.x;
+            if (d < td[15]) {
+              const int col = __float_as_int(v.y);
+              // Sorted insert without a dependency chain: the slot is counted with 16 independent compares and every
+              // entry is rewritten from the OLD values of itself and its left neighbour (descending s).
               int pos = 0;
 #pragma unroll
               for (int s = 0; s < 16; ++s) pos += (td[s] <= d) ? 1 : 0;
@@ -315,13 +310,66 @@ gemm2_f16_top16_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_co
             }
           }
         }
+        paddr = pend;
+      };
+      for (int nt = nt0; nt < nt0 + ntn; ++nt, ++it) {
+        const int as = C::ACC_BUFS == 2 ? (it & 1) : 0;
+        const uint32_t aphase = C::ACC_BUFS == 2 ? ((it >> 1) & 1) : (it & 1);
+        // Shared gate: the work items of one query block scan different database ranges concurrently, each keeping its
+        // own top-16.  An element that is not below the 16th-best distance ANY of them has already reached cannot be in
+        // the merged top-16, so every item publishes its 16th-best (atomicMin) after each tile and reads the common
+        // value before the next: the gate tightens with the UNION of the columns scanned so far.  A stale read only
+        // costs efficiency.  Ties at the gate are dropped: the guard's error bound covers them.
+        if (row_ok) {
+          const unsigned gv = *reinterpret_cast<volatile unsigned*>(g.gate + row);
+          if (gv != 0xFFFFFFFFu) thr = fminf(thr, d1_unord(gv));       // 0xFFFFFFFF = "no gate yet" (the memset pattern)
+        }
+        mbar_wait(&tfull_bar[as], aphase);
+        tc_fence_after();
+        const uint32_t t_row = tmem_base + ((uint32_t)(q * 32) << 16) + as * D1_BN;
+#pragma unroll 1
+        for (int ch = 0; ch < TILE_N / 32; ++ch) {
+          const int col0 = nt * TILE_N + ch * 32;
+          if (col0 >= g.n_valid) break;                    // warp-uniform: the rest of the tile is padding
+          // The per-column terms {|d|^2, 2^e} of this chunk: ONE coalesced load (lane j fetches column col0 + j) staged
+          // in shared memory and read back as warp-wide broadcasts.  A `__ldg(b_aux + col)` per column, as round 1's
+          // kernels did, is a chain of 256 dependent L2-latency loads per tile.
+          float2 mine = make_float2(INFINITY, 0.f);        // padding columns: +inf, never below the threshold
+          if (col0 + lane < g.n_valid) { const float4 t = __ldg(g.b_aux + col0 + lane); mine = make_float2(t.x, t.y); }
+          uint32_t raw[32];
+          tmem_ld_32x32(t_row + ch * 32, raw);
+          __syncwarp();                                    // the previous chunk's broadcast reads are done
+          d1_sts64(bst + lane * 8, mine.x, mine.y);
+          __syncwarp();
+          tmem_ld_wait();
+#pragma unroll
+          for (int h = 0; h < 2; ++h) {
+            if (__any_sync(0xffffffffu, paddr > pend + (D1_PEND - 16) * 1024)) {   // could overflow within 16 columns: merge first
+              merge_pending();
+              thr = fminf(thr, td[15]);
+            }
+            float2 c[16];
+#pragma unroll
+            for (int jj = 0; jj < 16; ++jj) c[jj] = d1_lds64(bst + (h * 16 + jj) * 8);   // issued back to back
+#pragma unroll
+            for (int jj = 0; jj < 16; ++jj) {
+              const int j = h * 16 + jj;
+              const float d = fmaf(m2sa * c[jj].y, __uint_as_float(raw[j]), an + c[jj].x);
+              if (d < thr) { d1_sts64(paddr, d, __int_as_float(col0 + j)); paddr += 1024; }
+            }
+          }
+        }
         tc_fence_before();
         __syncwarp();
         if (lane == 0) {
           if (leader) mbar_arrive(&tempty_bar[as]);
           else mbar_arrive_remote(mapa_u32(smem_u32(&tempty_bar[as]), 0));
         }
-        if (row_ok && td[15] < cap) atomicMin(g.gate + row, d1_ord(td[15]));
+        merge_pending();                                   // after the accumulator is released: overlaps the next main loop
+        if (row_ok && td[15] < thr) {
+          thr = td[15];
+          atomicMin(g.gate + row, d1_ord(thr));
+        }
       }
       if (row_ok) {
         const int sub = item % g.items_per_mpair;
