@@ -12,6 +12,12 @@ __device__ __forceinline__ uint32_t smem_u32(const void* p) {
   return static_cast<uint32_t>(__cvta_generic_to_shared(p));
 }
 
+// Warp-uniform copy of a value that every lane of the (converged) warp holds.  REDUX writes a UNIFORM register, so the
+// compiler keeps everything derived from the result on the uniform datapath; a value that came from a shared-memory
+// load or a special register is per-thread as far as it knows, and each tcgen05 instruction fed from it is wrapped in
+// an ELECT / R2UR.BROADCAST loop.
+__device__ __forceinline__ uint32_t warp_uniform(uint32_t v) { return __reduce_or_sync(0xffffffffu, v); }
+
 // ---- mbarrier -------------------------------------------------------------------------------
 __device__ __forceinline__ void mbar_init(uint64_t* bar, uint32_t count) {
   asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count) : "memory");
@@ -40,6 +46,30 @@ __device__ __forceinline__ bool mbar_try_wait(uint64_t* bar, uint32_t parity) {
 __device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
   while (!mbar_try_wait(bar, parity)) {
   }
+}
+// for a converged warp: lane 0 polls, the warp re-converges behind it (the polling loop is a divergent exit as far as
+// the compiler knows; without the re-convergence point everything after it is per-thread code)
+__device__ __forceinline__ void mbar_wait_warp(uint64_t* bar, uint32_t parity) {
+  if ((threadIdx.x & 31) == 0) mbar_wait(bar, parity);
+  __syncwarp();
+}
+// the same on a shared-space address (MMA-issuer warps keep barrier addresses as warp-uniform integers)
+__device__ __forceinline__ void mbar_wait_warp_a(uint32_t bar_addr, uint32_t parity) {
+  if ((threadIdx.x & 31) == 0) {
+    uint32_t ok;
+    do {
+      asm volatile(
+          "{\n\t"
+          ".reg .pred p;\n\t"
+          "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+          "selp.u32 %0, 1, 0, p;\n\t"
+          "}"
+          : "=r"(ok)
+          : "r"(bar_addr), "r"(parity)
+          : "memory");
+    } while (!ok);
+  }
+  __syncwarp();
 }
 __device__ __forceinline__ void fence_barrier_init() {
   asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
@@ -190,6 +220,10 @@ __device__ __forceinline__ void umma_commit(uint64_t* bar) {
                : "memory");
 }
 
+__device__ __forceinline__ void umma_commit_a(uint32_t bar_addr) {
+  asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(bar_addr) : "memory");
+}
+
 // same, arriving on the barrier at this offset in every CTA of the cluster selected by `mask`
 __device__ __forceinline__ void umma_commit_mc(uint64_t* bar, uint16_t mask) {
   asm volatile(
@@ -261,6 +295,12 @@ __device__ __forceinline__ void umma_commit_2sm_mc(uint64_t* bar, uint16_t mask)
   asm volatile(
       "tcgen05.commit.cta_group::2.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], %1;" ::"r"(
           smem_u32(bar)),
+      "h"(mask)
+      : "memory");
+}
+__device__ __forceinline__ void umma_commit_2sm_mc_a(uint32_t bar_addr, uint16_t mask) {
+  asm volatile(
+      "tcgen05.commit.cta_group::2.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], %1;" ::"r"(bar_addr),
       "h"(mask)
       : "memory");
 }

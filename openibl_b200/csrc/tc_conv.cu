@@ -395,98 +395,105 @@ conv3x3_tc_kernel(const __grid_constant__ CUtensorMap tm_xhi, const __grid_const
     }
   } else if (warp == 1) {
     // ================= MMA issuer =================
-    if (lane == 0 && leader) {
+    // The whole warp walks the schedule in convergent code and lane 0 alone executes the tcgen05 instructions; the ring
+    // position, the TMEM base and the shared-memory base pass through a REDUX (warp_uniform) once per stage, so every
+    // MMA operand and barrier address lives in a uniform register.  With the loop inside `if (lane == 0)` the compiler
+    // treated descriptors and TMEM addresses as per-thread values and wrapped EACH MMA in an ELECT + 5 x
+    // R2UR.BROADCAST loop: ~90 clk of dependent issue per MMA (ncu source view of the fused conv1 kernel), more than an
+    // N <= 128 MMA occupies the tensor pipe.
+    if (warp_uniform(leader ? 1u : 0u)) {
+      const bool issuer = lane == 0;
+      const uint32_t tmem_u = warp_uniform(tmem_base);
+      const uint32_t smem_a = warp_uniform(smem_u32(smem));
+      const uint32_t ring_a = smem_a + A_RING;
+      const uint32_t bars_a = ring_a + STAGES * STAGE_BYTES;
+      const uint32_t full_a = bars_a, empty_a = bars_a + 8 * STAGES;
+      const uint32_t tfull_a = bars_a + 16 * STAGES, tempty_a = tfull_a + 16;
+      const uint32_t afull_a = bars_a + 8 * (2 * STAGES + 5), aempty_a = afull_a + 8 * NA;
+      (void)afull_a; (void)aempty_a;
       constexpr uint32_t idesc = umma_idesc_bf16_f32(PAIR ? 2 * TC_BM : TC_BM, BN);
+      auto commit = [&](uint32_t bar) {
+        if (PAIR) umma_commit_2sm_mc_a(bar, 0x3);
+        else umma_commit_a(bar);
+      };
+      auto mma_step = [&](uint32_t d_tmem, uint64_t a_hi, uint64_t a_lo, uint64_t b_hi, uint64_t b_lo, bool fresh) {
+#pragma unroll
+        for (int k = 0; k < TC_BK / 16; ++k) {
+          // advance 16 bf16 = 32 bytes inside the 128-byte swizzle row: +2 in 16-byte units
+          const uint64_t ko = (uint64_t)(k * 2);
+          const uint32_t first = (!fresh || k > 0) ? 1u : 0u;
+          if (kConcat) {
+            constexpr uint32_t idesc2n = umma_idesc_bf16_f32(TC_BM, 2 * BN);
+            umma_bf16(d_tmem, a_hi + ko, b_hi + ko, idesc2n, first);          // [hi.hi | hi.lo]
+            umma_bf16(d_tmem + 2 * BN, a_lo + ko, b_hi + ko, idesc, first);   // lo.hi
+          } else if (PAIR) {
+            umma_bf16_2sm(d_tmem, a_lo + ko, b_hi + ko, idesc, first);
+            umma_bf16_2sm(d_tmem, a_hi + ko, b_lo + ko, idesc, 1u);
+            umma_bf16_2sm(d_tmem, a_hi + ko, b_hi + ko, idesc, 1u);
+          } else {
+            umma_bf16(d_tmem, a_lo + ko, b_hi + ko, idesc, first);
+            umma_bf16(d_tmem, a_hi + ko, b_lo + ko, idesc, 1u);
+            umma_bf16(d_tmem, a_hi + ko, b_hi + ko, idesc, 1u);
+          }
+        }
+      };
       int stage = 0, hstage = 0;
       uint32_t phase = 0, hphase = 0;
       (void)hstage; (void)hphase;
       int it = 0;
       for (int tile = worker; tile < a.total_tiles; tile += n_workers, ++it) {
-        const int as = it & 1;
+        const uint32_t as = warp_uniform((uint32_t)(it & 1));
         const uint32_t aphase = (it >> 1) & 1;
-        mbar_wait(&tempty_bar[as], aphase ^ 1);
+        mbar_wait_warp_a(tempty_a + 8 * as, aphase ^ 1);
         tc_fence_after();
-        const uint32_t d_tmem = tmem_base + as * ACC_COLS;
+        const uint32_t d_tmem = tmem_u + as * ACC_COLS;
         if constexpr (HALO) {
           // K-major SW128 view of the halo tile: 8-pixel row groups 10 rows apart
           constexpr uint64_t kHaloDesc = ((uint64_t)1 << 16) | ((uint64_t)((TC_HALO_W * 128) >> 4) << 32) |
                                          ((uint64_t)1 << 46) | ((uint64_t)2 << 61);
           for (int kc = 0; kc < kchunks; ++kc) {
-            mbar_wait(&afull_bar[hstage], hphase);
+            const uint32_t hs = warp_uniform((uint32_t)hstage);
+            mbar_wait_warp_a(afull_a + 8 * hs, hphase);
             tc_fence_after();
-            const uint32_t ha = smem_u32(smem + hstage * TC_HALO_STAGE);
+            const uint32_t ha = smem_a + hs * TC_HALO_STAGE;
             for (int tap = 0; tap < 9; ++tap) {
-              mbar_wait(&full_bar[stage], phase);
+              const uint32_t st = warp_uniform((uint32_t)stage);
+              mbar_wait_warp_a(full_a + 8 * st, phase);
               tc_fence_after();
               const uint32_t toff = (uint32_t)((tap / 3) * TC_HALO_W + tap % 3) * 128u;
               const uint64_t a_hi = kHaloDesc | (uint64_t)(((ha + toff) >> 4) & 0x3fffu);
               const uint64_t a_lo = kHaloDesc | (uint64_t)(((ha + TC_HALO_PLANE + toff) >> 4) & 0x3fffu);
-              const uint32_t sb = smem_u32(ring + stage * STAGE_BYTES);
-              const uint64_t b_hi = umma_desc_kmajor_sw128(sb);
-              const uint64_t b_lo = umma_desc_kmajor_sw128(sb + B_BYTES);
-#pragma unroll
-              for (int k = 0; k < TC_BK / 16; ++k) {
-                const uint64_t ko = (uint64_t)(k * 2);
-                const uint32_t first = (kc > 0 || tap > 0 || k > 0) ? 1u : 0u;
-                if (kConcat) {
-                  constexpr uint32_t idesc2n = umma_idesc_bf16_f32(TC_BM, 2 * BN);
-                  umma_bf16(d_tmem, a_hi + ko, b_hi + ko, idesc2n, first);
-                  umma_bf16(d_tmem + 2 * BN, a_lo + ko, b_hi + ko, idesc, first);
-                } else if (PAIR) {
-                  umma_bf16_2sm(d_tmem, a_lo + ko, b_hi + ko, idesc, first);
-                  umma_bf16_2sm(d_tmem, a_hi + ko, b_lo + ko, idesc, 1u);
-                  umma_bf16_2sm(d_tmem, a_hi + ko, b_hi + ko, idesc, 1u);
-                } else {
-                  umma_bf16(d_tmem, a_lo + ko, b_hi + ko, idesc, first);
-                  umma_bf16(d_tmem, a_hi + ko, b_lo + ko, idesc, 1u);
-                  umma_bf16(d_tmem, a_hi + ko, b_hi + ko, idesc, 1u);
-                }
+              const uint32_t sb = ring_a + st * STAGE_BYTES;
+              if (issuer) {
+                mma_step(d_tmem, a_hi, a_lo, umma_desc_kmajor_sw128(sb), umma_desc_kmajor_sw128(sb + B_BYTES),
+                         kc == 0 && tap == 0);
+                commit(empty_a + 8 * st);           // frees the weight slot (in both CTAs of a pair) when these MMAs retire
               }
-              if (PAIR) umma_commit_2sm_mc(&empty_bar[stage], 0x3);
-              else umma_commit(&empty_bar[stage]);
+              __syncwarp();
               if (++stage == STAGES) { stage = 0; phase ^= 1; }
             }
-            if (PAIR) umma_commit_2sm_mc(&aempty_bar[hstage], 0x3);
-            else umma_commit(&aempty_bar[hstage]);
+            if (issuer) commit(aempty_a + 8 * hs);
+            __syncwarp();
             if (++hstage == NA) { hstage = 0; hphase ^= 1; }
           }
         } else {
-        for (int kit = 0; kit < kiters; ++kit) {
-          mbar_wait(&full_bar[stage], phase);
-          tc_fence_after();
-          const uint32_t sa = smem_u32(smem + stage * STAGE_BYTES);
-          const uint64_t a_hi = umma_desc_kmajor_sw128(sa);
-          const uint64_t a_lo = umma_desc_kmajor_sw128(sa + TC_A_BYTES);
-          const uint64_t b_hi = umma_desc_kmajor_sw128(sa + 2 * TC_A_BYTES);
-          const uint64_t b_lo = umma_desc_kmajor_sw128(sa + 2 * TC_A_BYTES + B_BYTES);
-#pragma unroll
-          for (int k = 0; k < TC_BK / 16; ++k) {
-            // advance 16 bf16 = 32 bytes inside the 128-byte swizzle row: +2 in 16-byte units
-            const uint64_t ko = (uint64_t)(k * 2);
-            const uint32_t first = (kit > 0 || k > 0) ? 1u : 0u;
-            if (kConcat) {
-              constexpr uint32_t idesc2n = umma_idesc_bf16_f32(TC_BM, 2 * BN);
-              umma_bf16(d_tmem, a_hi + ko, b_hi + ko, idesc2n, first);          // [hi.hi | hi.lo]
-              umma_bf16(d_tmem + 2 * BN, a_lo + ko, b_hi + ko, idesc, first);   // lo.hi
-            } else if (PAIR) {
-              umma_bf16_2sm(d_tmem, a_lo + ko, b_hi + ko, idesc, first);
-              umma_bf16_2sm(d_tmem, a_hi + ko, b_lo + ko, idesc, 1u);
-              umma_bf16_2sm(d_tmem, a_hi + ko, b_hi + ko, idesc, 1u);
-            } else {
-              umma_bf16(d_tmem, a_lo + ko, b_hi + ko, idesc, first);
-              umma_bf16(d_tmem, a_hi + ko, b_lo + ko, idesc, 1u);
-              umma_bf16(d_tmem, a_hi + ko, b_hi + ko, idesc, 1u);
+          for (int kit = 0; kit < kiters; ++kit) {
+            const uint32_t st = warp_uniform((uint32_t)stage);
+            mbar_wait_warp_a(full_a + 8 * st, phase);
+            tc_fence_after();
+            const uint32_t sa = smem_a + st * STAGE_BYTES;
+            if (issuer) {
+              mma_step(d_tmem, umma_desc_kmajor_sw128(sa), umma_desc_kmajor_sw128(sa + TC_A_BYTES),
+                       umma_desc_kmajor_sw128(sa + 2 * TC_A_BYTES), umma_desc_kmajor_sw128(sa + 2 * TC_A_BYTES + B_BYTES),
+                       kit == 0);
+              commit(empty_a + 8 * st);             // frees the smem slot (in both CTAs of a pair) when these MMAs retire
             }
+            __syncwarp();
+            if (++stage == STAGES) { stage = 0; phase ^= 1; }
           }
-          // frees the smem slot (in both CTAs of a pair) when these MMAs retire
-          if (PAIR) umma_commit_2sm_mc(&empty_bar[stage], 0x3);
-          else umma_commit(&empty_bar[stage]);
-          if (++stage == STAGES) { stage = 0; phase ^= 1; }
         }
-        }
-        // accumulator ready for the epilogue
-        if (PAIR) umma_commit_2sm_mc(&tfull_bar[as], 0x3);
-        else umma_commit(&tfull_bar[as]);
+        if (issuer) commit(tfull_a + 8 * as);       // accumulator ready for the epilogue
+        __syncwarp();
       }
     }
   } else {
@@ -771,7 +778,11 @@ conv1_fused_tc_kernel(const __grid_constant__ CUtensorMap tm_whi, const __grid_c
   tc_fence_before();
   __syncthreads();
   tc_fence_after();
-  const uint32_t tmem_base = *tmem_slot;
+  // All 512 columns are allocated, so the allocation starts at column 0 of lane 0: address 0.  A compile-time constant
+  // keeps every TMEM operand of the MMAs in a uniform register (a value loaded from shared memory is per-thread as far
+  // as the compiler knows, and each MMA then pays an ELECT / R2UR.BROADCAST loop).
+  if (*tmem_slot != 0u) __trap();
+  constexpr uint32_t tmem_base = 0u;
   const uint32_t t_acc1 = tmem_base + 384;            // M tile 0: columns 384-447, M tile 1: 448-511
   constexpr uint32_t ACC2_COLS = 192;
   const int tiles_per_img = a.tiles_h * a.tiles_w;
@@ -800,7 +811,14 @@ conv1_fused_tc_kernel(const __grid_constant__ CUtensorMap tm_whi, const __grid_c
     }
   } else if (warp == 1) {
     // ================= MMA issuer =================
-    if (lane == 0) {
+    // The WHOLE warp walks the schedule (waits included) and lane 0 alone executes the tcgen05 instructions: every
+    // operand is then computed in convergent code from warp-uniform values and lives in uniform registers.  With the
+    // loop inside `if (lane == 0)` the compiler treated tmem addresses and descriptors as per-thread values and wrapped
+    // each MMA in an ELECT / R2UR.BROADCAST "waterfall" loop: ~90 clk of dependent issue per MMA (ncu source view),
+    // more than the 32-65 clk an N = 64 / 128 MMA occupies the tensor pipe -- the kernel was issue-bound at 40 %
+    // tensor-pipe activity.
+    {
+      const bool issuer = lane == 0;
       constexpr uint32_t idesc64 = umma_idesc_bf16_f32(TC_BM, 64);
       constexpr uint32_t idesc128 = umma_idesc_bf16_f32(TC_BM, 128);
       constexpr uint64_t kHaloDesc = ((uint64_t)1 << 16) | ((uint64_t)((TC_HALO_W * 128) >> 4) << 32) |
@@ -820,13 +838,18 @@ conv1_fused_tc_kernel(const __grid_constant__ CUtensorMap tm_whi, const __grid_c
 #pragma unroll
           for (int k = 0; k < 2; ++k) {               // K = 32: two 16-wide steps
             const uint64_t ko = (uint64_t)(k * 2);
-            umma_bf16(d, al + ko, b1h + ko, idesc64, k > 0 ? 1u : 0u);
-            umma_bf16(d, ah + ko, b1l + ko, idesc64, 1u);
-            umma_bf16(d, ah + ko, b1h + ko, idesc64, 1u);
+            if (issuer) {
+              umma_bf16(d, al + ko, b1h + ko, idesc64, k > 0 ? 1u : 0u);
+              umma_bf16(d, ah + ko, b1l + ko, idesc64, 1u);
+              umma_bf16(d, ah + ko, b1h + ko, idesc64, 1u);
+            }
           }
         }
-        umma_commit(a1_empty);
-        umma_commit(acc1_full);
+        if (issuer) {
+          umma_commit(a1_empty);
+          umma_commit(acc1_full);
+        }
+        __syncwarp();
       };
       int stage = 0; uint32_t phase = 0;
       if (n_tiles > 0) issue_c1(0);
@@ -847,18 +870,24 @@ conv1_fused_tc_kernel(const __grid_constant__ CUtensorMap tm_whi, const __grid_c
           const uint64_t a_lo = kHaloDesc | (uint64_t)(((ha + TC_HALO_PLANE + toff) >> 4) & 0x3fffu);
           const uint32_t sb = smem_u32(w2 + stage * F1_W2_STAGE);
           const uint64_t b_cat = umma_desc_kmajor_sw128(sb);          // 128 rows: W_hi then W_lo
+          if (issuer) {
 #pragma unroll
-          for (int k = 0; k < TC_BK / 16; ++k) {
-            const uint64_t ko = (uint64_t)(k * 2);
-            const uint32_t first = (tap > 0 || k > 0) ? 1u : 0u;
-            umma_bf16(d_tmem, a_hi + ko, b_cat + ko, idesc128, first);            // [hi.hi | hi.lo]
-            umma_bf16(d_tmem + 128, a_lo + ko, b_cat + ko, idesc64, first);       // lo.hi
+            for (int k = 0; k < TC_BK / 16; ++k) {
+              const uint64_t ko = (uint64_t)(k * 2);
+              const uint32_t first = (tap > 0 || k > 0) ? 1u : 0u;
+              umma_bf16(d_tmem, a_hi + ko, b_cat + ko, idesc128, first);            // [hi.hi | hi.lo]
+              umma_bf16(d_tmem + 128, a_lo + ko, b_cat + ko, idesc64, first);       // lo.hi
+            }
+            umma_commit(&w_empty[stage]);
           }
-          umma_commit(&w_empty[stage]);
+          __syncwarp();
           if (++stage == F1_W2_STAGES) { stage = 0; phase ^= 1; }
         }
-        umma_commit(&halo_empty[hb]);
-        umma_commit(&acc2_full[hb]);
+        if (issuer) {
+          umma_commit(&halo_empty[hb]);
+          umma_commit(&acc2_full[hb]);
+        }
+        __syncwarp();
       }
     }
   } else if (warp <= 5) {

@@ -132,11 +132,11 @@ constexpr int D1_PEND = 32;                            // pending candidates per
 constexpr int D1_A_BYTES = 128 * D1_BK * 2;            // 16 KiB: this CTA's 128 query rows
 constexpr int D1_BH_BYTES = (D1_BN / 2) * D1_BK * 2;   // 16 KiB: this CTA's half of one 256-row database sub-tile
 
-// SUB = 256-row database sub-tiles per work tile.  One fp16 pass needs 64 B/clk/SM of operands at 256 x 256 per SM
-// pair -- more than the L2 delivers (~43 B/clk/SM chip-wide) -- so the default is SUB = 2: a 256 x 512 tile reuses
-// every staged query block for two MMAs (48 KiB per stage instead of 2 x 32), with ONE 512-column accumulator: the
-// epilogue of a tile is not overlapped with the next main loop (~5 % of a K = 4096 tile).  SUB = 1 keeps two
-// 256-column accumulators and overlaps them.
+// SUB = 256-row database sub-tiles per work tile.  SUB = 1 (default): 256 x 256 tiles, two 256-column accumulators, the
+// epilogue of tile i runs under the main loop of tile i+1.  SUB = 2 (IBL_DIST_BN=512): a 256 x 512 tile reuses every
+// staged query block for two MMAs (48 KiB per stage instead of 2 x 32: 25 % less L2->SM traffic) but has ONE 512-column
+// accumulator, so epilogue and main loop alternate.  Measured (profiles/r02_dist_variants_s8.jsonl, whole call,
+// 6.8k x {10k, 31k, 250k} x 4096): SUB = 1 0.70 / 1.62 / 11.9 ms, SUB = 2 0.79 / 1.80 / 12.4 ms.
 template <int SUB> struct D1Cfg {
   static constexpr int STAGES = SUB == 1 ? 6 : 4;
   static constexpr int STAGE = D1_A_BYTES + SUB * D1_BH_BYTES;
@@ -151,10 +151,13 @@ template <int SUB> struct D1Cfg {
 // SM pairs: the peer CTA's producer does NOT arrive on the leader's full barrier.  The leader's single
 // arrive.expect_tx names the bytes of BOTH CTAs; the peer's TMA completions decrement the same transaction count
 // (complete_tx may land before the expect_tx: the phase still cannot complete before the leader's arrival).  Round 1
-// had the peer do an `mbarrier.arrive.release.cluster` per stage: that release fence waits for the peer's outstanding
-// bulk copies, which serialised its loads (~1 us per stage; ncu: 12 % tensor-pipe active on the single-pass distance
-// kernel, 13 % of L2 throughput).  The peer cannot lap the ring: it waits on its local empty barrier, which the
-// leader's multicast commit signals.
+// had the peer do an `mbarrier.arrive.release.cluster` per stage; removing it was worth ~2 %.  The peer cannot lap the
+// ring: it waits on its local empty barrier, which the leader's multicast commit signals.
+//
+// What actually bounded this kernel (ncu source view, profiles/r02_dist_f16_v{2,3,4}*.md): the EPILOGUE.  At 10 k
+// database rows per query the sorted insertion ran for half of all columns (any of a warp's 32 rows inserting) at
+// ~110 instructions a time, one warp per scheduler: 968 us with the tensor pipe 27 % active.  The pending-list epilogue
+// below brought the kernel to the MMA/L2 bound (whole call 1.24 -> 0.70 ms).
 template <int SUB>
 __global__ void __launch_bounds__(192, 1)
 gemm2_f16_top16_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constant__ CUtensorMap tm_b,
@@ -221,37 +224,50 @@ gemm2_f16_top16_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_co
       }
     }
   } else if (warp == 1) {
-    if (leader && lane == 0) {
+    // whole warp in convergent code, lane 0 issues, ring position / bases warp-uniform: every tcgen05 operand lives in a
+    // uniform register (tc_conv.cu, MMA issuer)
+    if (warp_uniform(leader ? 1u : 0u)) {
+      const bool issuer = lane == 0;
       constexpr uint32_t idesc = umma_idesc_f16_f32(256, D1_BN);
+      const uint32_t tmem_u = warp_uniform(tmem_base);
+      const uint32_t smem_a = warp_uniform(smem_u32(smem));
+      const uint32_t bars_a = smem_a + STAGES * STAGE;
+      const uint32_t full_a = bars_a, empty_a = bars_a + 8 * STAGES;
+      const uint32_t tfull_a = bars_a + 16 * STAGES, tempty_a = tfull_a + 16;
       int stage = 0; uint32_t phase = 0;
       int it = 0;
       for (int item = unit0; item < g.total_items; item += unit_stride) {
         int mp, nt0, ntn;
         decode(item, mp, nt0, ntn);
         for (int nt = nt0; nt < nt0 + ntn; ++nt, ++it) {
-          const int as = C::ACC_BUFS == 2 ? (it & 1) : 0;
+          const uint32_t as = warp_uniform((uint32_t)(C::ACC_BUFS == 2 ? (it & 1) : 0));
           const uint32_t aphase = C::ACC_BUFS == 2 ? ((it >> 1) & 1) : (it & 1);
-          mbar_wait(&tempty_bar[as], aphase ^ 1);
+          mbar_wait_warp_a(tempty_a + 8 * as, aphase ^ 1);
           tc_fence_after();
-          const uint32_t d_tmem = tmem_base + as * D1_BN;
+          const uint32_t d_tmem = tmem_u + as * D1_BN;
           for (int kit = 0; kit < kiters; ++kit) {
-            mbar_wait(&full_bar[stage], phase);
+            const uint32_t st = warp_uniform((uint32_t)stage);
+            mbar_wait_warp_a(full_a + 8 * st, phase);
             tc_fence_after();
-            const uint32_t sa = smem_u32(smem + stage * STAGE);
-            const uint64_t a = umma_desc_kmajor_sw128(sa);
+            const uint32_t sa = smem_a + st * STAGE;
+            if (issuer) {
+              const uint64_t a = umma_desc_kmajor_sw128(sa);
 #pragma unroll
-            for (int k = 0; k < D1_BK / 16; ++k) {
+              for (int k = 0; k < D1_BK / 16; ++k) {
 #pragma unroll
-              for (int j = 0; j < SUB; ++j) {
-                const uint64_t b = umma_desc_kmajor_sw128(sa + D1_A_BYTES + j * D1_BH_BYTES);
-                umma_bf16_2sm(d_tmem + j * D1_BN, a + (uint64_t)(k * 2), b + (uint64_t)(k * 2), idesc,
-                              (kit > 0 || k > 0) ? 1u : 0u);
+                for (int j = 0; j < SUB; ++j) {
+                  const uint64_t b = umma_desc_kmajor_sw128(sa + D1_A_BYTES + j * D1_BH_BYTES);
+                  umma_bf16_2sm(d_tmem + j * D1_BN, a + (uint64_t)(k * 2), b + (uint64_t)(k * 2), idesc,
+                                (kit > 0 || k > 0) ? 1u : 0u);
+                }
               }
+              umma_commit_2sm_mc_a(empty_a + 8 * st, 0x3);
             }
-            umma_commit_2sm_mc(&empty_bar[stage], 0x3);
+            __syncwarp();
             if (++stage == STAGES) { stage = 0; phase ^= 1; }
           }
-          umma_commit_2sm_mc(&tfull_bar[as], 0x3);
+          if (issuer) umma_commit_2sm_mc_a(tfull_a + 8 * as, 0x3);
+          __syncwarp();
         }
       }
     }
@@ -684,7 +700,7 @@ int launch_dist_topk_1pass(const float* q, int m, const float* db, int n, int n_
     IBL_RET(make_tmap(&mb, CU_TENSOR_MAP_DATA_TYPE_FLOAT16, 2, dp, dims_b, str, box));
   }
   // IBL_DIST_BN=256 selects the 256 x 256 tile with two overlapped accumulators (A/B measurements, variant tests)
-  static const int tile_env = [] { const char* v = getenv("IBL_DIST_BN"); return v ? atoi(v) : 512; }();
+  static const int tile_env = [] { const char* v = getenv("IBL_DIST_BN"); return v ? atoi(v) : 256; }();
   const int SUBn = tile_env == 256 ? 1 : 2;
   Dist1Args g{};
   g.M = m; g.N = n; g.K = d;
