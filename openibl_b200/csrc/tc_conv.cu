@@ -145,7 +145,7 @@ __device__ __forceinline__ void conv_epilogue_tile(const ConvTcArgs& a, uint32_t
   if (a.pool) {
     const int OH = a.H >> 1, OW = a.W >> 1;
     const int oh = h >> 1, ow = w >> 1;
-    valid = ((r & 1) == 0) && ((c & 1) == 0) && oh < OH && ow < OW && img < a.N;
+    valid = oh < OH && ow < OW && img < a.N;      // all four lanes of a window store (8 channels each per 32-channel chunk)
     pix = ((long long)img * OH + oh) * OW + ow;
   } else {
     valid = h < a.H && w < a.W && img < a.N;
@@ -166,6 +166,57 @@ __device__ __forceinline__ void conv_epilogue_tile(const ConvTcArgs& a, uint32_t
         raw[j] = __float_as_uint((__uint_as_float(r1[j]) + __uint_as_float(r2[j])) + __uint_as_float(raw[j]));
     }
     tmem_ld_wait();
+    if (a.pool) {
+      // 2x2 max-pool BEFORE bias / ReLU / split (fmaf(., scale > 0, b) and max(., 0) are monotone, so the results are
+      // the same bits) as a two-step exchange: against the w-neighbour (lane ^ 1) every lane keeps one half of the 32
+      // channels and sends the other, against the h-neighbour (lane ^ TW) one half of those 16 -- 24 shuffles instead
+      // of 64, and each of the window's four lanes finishes 8 channels (bias, ReLU, hi/lo, ONE 16-byte store per plane)
+      // instead of one lane doing all 32 while three idle.
+      const bool s1 = (c & 1) != 0, s2 = (r & 1) != 0;
+      float u[16];
+#pragma unroll
+      for (int j = 0; j < 16; ++j) {
+        const float lo_h = __uint_as_float(raw[j]), hi_h = __uint_as_float(raw[j + 16]);
+        const float got = __shfl_xor_sync(0xffffffffu, s1 ? lo_h : hi_h, 1);
+        u[j] = fmaxf(s1 ? hi_h : lo_h, got);
+      }
+      float w8[8];
+#pragma unroll
+      for (int j = 0; j < 8; ++j) {
+        const float got = __shfl_xor_sync(0xffffffffu, s2 ? u[j] : u[j + 8], TW);
+        w8[j] = fmaxf(s2 ? u[j + 8] : u[j], got);
+      }
+      if (valid) {
+        const int cbase = n0 + ch * 32 + (s1 ? 16 : 0) + (s2 ? 8 : 0);
+        const float4 b0 = __ldg(reinterpret_cast<const float4*>(a.bias + cbase));
+        const float4 b1 = __ldg(reinterpret_cast<const float4*>(a.bias + cbase) + 1);
+        const float bb[8] = {b0.x, b0.y, b0.z, b0.w, b1.x, b1.y, b1.z, b1.w};
+#pragma unroll
+        for (int j = 0; j < 8; ++j) {
+          w8[j] = fmaf(w8[j], a.acc_scale, bb[j]);
+          if (a.relu) w8[j] = fmaxf(w8[j], 0.f);
+        }
+        const long long off = pix * a.cout + cbase;
+        if (a.y_f32) {
+          float4* o = reinterpret_cast<float4*>(a.y_f32 + off);
+          o[0] = make_float4(w8[0], w8[1], w8[2], w8[3]);
+          o[1] = make_float4(w8[4], w8[5], w8[6], w8[7]);
+        } else {
+          uint32_t hi[4], lo[4];
+#pragma unroll
+          for (int j = 0; j < 4; ++j) {
+            const float x0 = w8[2 * j], x1 = w8[2 * j + 1];
+            const __nv_bfloat16 h0b = __float2bfloat16_rn(x0), h1b = __float2bfloat16_rn(x1);
+            __nv_bfloat162 hh(h0b, h1b);
+            hi[j] = *reinterpret_cast<uint32_t*>(&hh);
+            lo[j] = pack_bf16x2(x0 - __bfloat162float(h0b), x1 - __bfloat162float(h1b));
+          }
+          *reinterpret_cast<uint4*>(a.y_hi + off) = make_uint4(hi[0], hi[1], hi[2], hi[3]);
+          *reinterpret_cast<uint4*>(a.y_lo + off) = make_uint4(lo[0], lo[1], lo[2], lo[3]);
+        }
+      }
+      continue;
+    }
     float v[32];
     const float4* bp = reinterpret_cast<const float4*>(a.bias + n0 + ch * 32);
 #pragma unroll
@@ -183,13 +234,6 @@ __device__ __forceinline__ void conv_epilogue_tile(const ConvTcArgs& a, uint32_t
     if (a.ssq) {
 #pragma unroll
       for (int j = 0; j < 32; ++j) ssq_acc = fmaf(v[j], v[j], ssq_acc);
-    }
-    if (a.pool) {
-#pragma unroll
-      for (int j = 0; j < 32; ++j) {
-        v[j] = fmaxf(v[j], __shfl_xor_sync(0xffffffffu, v[j], 1));
-        v[j] = fmaxf(v[j], __shfl_xor_sync(0xffffffffu, v[j], TW));
-      }
     }
     if (valid) {
       const long long off = pix * a.cout + n0 + ch * 32;
@@ -298,99 +342,135 @@ conv3x3_tc_kernel(const __grid_constant__ CUtensorMap tm_xhi, const __grid_const
 
   if (warp == 0) {
     // ================= TMA producer =================
-    if (lane == 0) {
+    // same discipline as the MMA issuer below: convergent warp, lane 0 issues, ring positions / coordinates warp-uniform
+    {
+      const bool issuer = lane == 0;
+      const uint32_t smem_a = warp_uniform(smem_u32(smem));
+      const uint32_t ring_a = smem_a + A_RING;
+      const uint32_t bars_a = ring_a + STAGES * STAGE_BYTES;
+      const uint32_t full_a = bars_a, empty_a = bars_a + 8 * STAGES;
+      const uint32_t afull_a = bars_a + 8 * (2 * STAGES + 5), aempty_a = afull_a + 8 * NA;
+      // pair: all bytes of a stage are accounted on the LEADER's barrier, named by its shared::cluster address
+      const uint32_t full_c = PAIR ? warp_uniform(mapa_u32(full_a, 0)) : full_a;
+      const uint32_t afull_c = PAIR ? warp_uniform(mapa_u32(afull_a, 0)) : afull_a;
+      (void)afull_a; (void)aempty_a; (void)afull_c;
+      const uint32_t rank_u = warp_uniform(rank);
       int stage = 0, astage = 0;
       uint32_t phase = 0, aphase = 0;
       (void)astage; (void)aphase;
+      auto coords = [&](int tile, int& img, int& h0, int& w0, int& n0) {
+        const int nt = tile % a.n_tiles;
+        const int pt = PAIR ? 2 * (tile / a.n_tiles) + (int)rank_u : tile / a.n_tiles;
+        img = pt / tiles_per_img;               // pair: an odd patch count leaves img == N for the last peer:
+        const int rem = pt - img * tiles_per_img;     // TMA zero-fills, the epilogue stores nothing
+        h0 = (rem / a.tiles_w) * (TC_BM >> a.tw_log2);
+        w0 = (rem % a.tiles_w) * TW;
+        n0 = PAIR ? nt * BN + (int)rank_u * (BN / 2) : nt * BN;
+        img = (int)warp_uniform((uint32_t)img); h0 = (int)warp_uniform((uint32_t)h0);
+        w0 = (int)warp_uniform((uint32_t)w0); n0 = (int)warp_uniform((uint32_t)n0);
+      };
+      // lane 0 polls once; the answer is broadcast so that the branch on it is warp-uniform
+      auto try_wait_warp = [&](uint32_t bar, uint32_t parity) -> bool {
+        uint32_t ok = 0;
+        if (issuer) {
+          asm volatile(
+              "{\n\t"
+              ".reg .pred p;\n\t"
+              "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+              "selp.u32 %0, 1, 0, p;\n\t"
+              "}"
+              : "=r"(ok)
+              : "r"(bar), "r"(parity)
+              : "memory");
+        }
+        return warp_uniform(ok) != 0;
+      };
+      (void)try_wait_warp;
       if constexpr (HALO) {
         // Two independent streams -- halo tiles (one per tile and 64-channel chunk) and weight taps (nine per
         // halo) -- each issued as soon as its ring has a free slot, so the halo of the NEXT chunk is in flight
         // while the taps of the current one are still being fed.
-        auto coords = [&](int tile, int& img, int& h0, int& w0, int& n0) {
-          const int nt = tile % a.n_tiles;
-          const int pt = PAIR ? 2 * (tile / a.n_tiles) + (int)rank : tile / a.n_tiles;
-          img = pt / tiles_per_img;             // pair: an odd patch count leaves img == N for the last peer:
-          const int rem = pt - img * tiles_per_img;   // TMA zero-fills, the epilogue stores nothing
-          h0 = (rem / a.tiles_w) * (TC_BM >> a.tw_log2);
-          w0 = (rem % a.tiles_w) * TW;
-          n0 = PAIR ? nt * BN + (int)rank * (BN / 2) : nt * BN;
-        };
         int tA = worker, kcA = 0, tB = worker, kcB = 0, tapB = 0;
         while (tB < a.total_tiles) {
-          if (tA < a.total_tiles && mbar_try_wait(&aempty_bar[astage], aphase ^ 1)) {
+          const uint32_t as_u = warp_uniform((uint32_t)astage);
+          if (tA < a.total_tiles && try_wait_warp(aempty_a + 8 * as_u, aphase ^ 1)) {
             int img, h0, w0, n0;
             coords(tA, img, h0, w0, n0);
             (void)n0;
-            const int c0 = kcA * TC_BK;
-            uint8_t* sa = smem + astage * TC_HALO_STAGE;
+            const int c0 = (int)warp_uniform((uint32_t)(kcA * TC_BK));
+            const uint32_t sa = smem_a + as_u * TC_HALO_STAGE;
             constexpr uint32_t kHaloBytes = 2u * TC_HALO_W * TC_HALO_H * 128u;
-            if (PAIR) {
-              const uint32_t lead = mapa_u32(smem_u32(&afull_bar[astage]), 0);
-              if (leader) mbar_arrive_expect_tx(&afull_bar[astage], 2 * kHaloBytes);
-              tma_load_4d_2sm(sa, &tm_xhi, lead, c0, w0 - 1, h0 - 1, img);
-              tma_load_4d_2sm(sa + TC_HALO_PLANE, &tm_xlo, lead, c0, w0 - 1, h0 - 1, img);
-            } else {
-              mbar_arrive_expect_tx(&afull_bar[astage], kHaloBytes);
-              tma_load_4d(sa, &tm_xhi, &afull_bar[astage], c0, w0 - 1, h0 - 1, img);
-              tma_load_4d(sa + TC_HALO_PLANE, &tm_xlo, &afull_bar[astage], c0, w0 - 1, h0 - 1, img);
+            if (issuer) {
+              if (PAIR) {
+                if (leader) mbar_arrive_expect_tx_a(afull_a + 8 * as_u, 2 * kHaloBytes);
+                tma_load_4d_2sm_a(sa, &tm_xhi, afull_c + 8 * as_u, c0, w0 - 1, h0 - 1, img);
+                tma_load_4d_2sm_a(sa + TC_HALO_PLANE, &tm_xlo, afull_c + 8 * as_u, c0, w0 - 1, h0 - 1, img);
+              } else {
+                mbar_arrive_expect_tx_a(afull_a + 8 * as_u, kHaloBytes);
+                tma_load_4d_a(sa, &tm_xhi, afull_a + 8 * as_u, c0, w0 - 1, h0 - 1, img);
+                tma_load_4d_a(sa + TC_HALO_PLANE, &tm_xlo, afull_a + 8 * as_u, c0, w0 - 1, h0 - 1, img);
+              }
             }
+            __syncwarp();
             if (++astage == NA) { astage = 0; aphase ^= 1; }
             if (++kcA == kchunks) { kcA = 0; tA += n_workers; }
             continue;
           }
-          if (mbar_try_wait(&empty_bar[stage], phase ^ 1)) {
+          const uint32_t st_u = warp_uniform((uint32_t)stage);
+          if (try_wait_warp(empty_a + 8 * st_u, phase ^ 1)) {
             int img, h0, w0, n0;
             coords(tB, img, h0, w0, n0);
-            const int c0 = kcB * TC_BK;
-            uint8_t* st = ring + stage * STAGE_BYTES;
-            if (PAIR) {
-              const uint32_t lead_full = mapa_u32(smem_u32(&full_bar[stage]), 0);
-              if (leader) mbar_arrive_expect_tx(&full_bar[stage], 2 * STAGE_BYTES);
-              tma_load_3d_2sm(st, &tm_whi, lead_full, c0, n0, tapB);
-              tma_load_3d_2sm(st + B_BYTES, &tm_wlo, lead_full, c0, n0, tapB);
-            } else {
-              mbar_arrive_expect_tx(&full_bar[stage], STAGE_BYTES);
-              tma_load_3d(st, &tm_whi, &full_bar[stage], c0, n0, tapB);
-              tma_load_3d(st + B_BYTES, &tm_wlo, &full_bar[stage], c0, n0, tapB);
+            const int c0 = (int)warp_uniform((uint32_t)(kcB * TC_BK));
+            const int tap = (int)warp_uniform((uint32_t)tapB);
+            const uint32_t st = ring_a + st_u * STAGE_BYTES;
+            if (issuer) {
+              if (PAIR) {
+                if (leader) mbar_arrive_expect_tx_a(full_a + 8 * st_u, 2 * STAGE_BYTES);
+                tma_load_3d_2sm_a(st, &tm_whi, full_c + 8 * st_u, c0, n0, tap);
+                tma_load_3d_2sm_a(st + B_BYTES, &tm_wlo, full_c + 8 * st_u, c0, n0, tap);
+              } else {
+                mbar_arrive_expect_tx_a(full_a + 8 * st_u, STAGE_BYTES);
+                tma_load_3d_a(st, &tm_whi, full_a + 8 * st_u, c0, n0, tap);
+                tma_load_3d_a(st + B_BYTES, &tm_wlo, full_a + 8 * st_u, c0, n0, tap);
+              }
             }
+            __syncwarp();
             if (++stage == STAGES) { stage = 0; phase ^= 1; }
             if (++tapB == 9) { tapB = 0; if (++kcB == kchunks) { kcB = 0; tB += n_workers; } }
           }
         }
       } else {
-      for (int tile = worker; tile < a.total_tiles; tile += n_workers) {
-        const int nt = tile % a.n_tiles;
-        const int pt = PAIR ? 2 * (tile / a.n_tiles) + (int)rank : tile / a.n_tiles;
-        const int img = pt / tiles_per_img;     // pair: an odd patch count leaves img == N for the last
-        const int rem = pt - img * tiles_per_img;   // peer: TMA zero-fills, the epilogue stores nothing
-        const int h0 = (rem / a.tiles_w) * (TC_BM >> a.tw_log2);
-        const int w0 = (rem % a.tiles_w) * TW;
-        const int n0 = PAIR ? nt * BN + (int)rank * (BN / 2) : nt * BN;
-        {
-        for (int kit = 0; kit < kiters; ++kit) {
-          const int tap = kit / kchunks;
-          const int c0 = (kit - tap * kchunks) * TC_BK;
-          const int kh = tap / 3 - 1, kw = tap % 3 - 1;
-          mbar_wait(&empty_bar[stage], phase ^ 1);
-          uint8_t* st = smem + stage * STAGE_BYTES;
-          if (PAIR) {
-            const uint32_t lead_full = mapa_u32(smem_u32(&full_bar[stage]), 0);
-            if (leader) mbar_arrive_expect_tx(&full_bar[stage], 2 * STAGE_BYTES);   // bytes of both CTAs
-            tma_load_4d_2sm(st, &tm_xhi, lead_full, c0, w0 + kw, h0 + kh, img);
-            tma_load_4d_2sm(st + TC_A_BYTES, &tm_xlo, lead_full, c0, w0 + kw, h0 + kh, img);
-            tma_load_3d_2sm(st + 2 * TC_A_BYTES, &tm_whi, lead_full, c0, n0, tap);
-            tma_load_3d_2sm(st + 2 * TC_A_BYTES + B_BYTES, &tm_wlo, lead_full, c0, n0, tap);
-          } else {
-            mbar_arrive_expect_tx(&full_bar[stage], STAGE_BYTES);
-            tma_load_4d(st, &tm_xhi, &full_bar[stage], c0, w0 + kw, h0 + kh, img);
-            tma_load_4d(st + TC_A_BYTES, &tm_xlo, &full_bar[stage], c0, w0 + kw, h0 + kh, img);
-            tma_load_3d(st + 2 * TC_A_BYTES, &tm_whi, &full_bar[stage], c0, n0, tap);
-            tma_load_3d(st + 2 * TC_A_BYTES + B_BYTES, &tm_wlo, &full_bar[stage], c0, n0, tap);
+        for (int tile = worker; tile < a.total_tiles; tile += n_workers) {
+          int img, h0, w0, n0;
+          coords(tile, img, h0, w0, n0);
+          for (int kit = 0; kit < kiters; ++kit) {
+            const int tap = (int)warp_uniform((uint32_t)(kit / kchunks));
+            const int c0 = (int)warp_uniform((uint32_t)((kit - tap * kchunks) * TC_BK));
+            const int kh = tap / 3 - 1, kw = tap % 3 - 1;
+            const uint32_t st_u = warp_uniform((uint32_t)stage);
+            mbar_wait_warp_a(empty_a + 8 * st_u, phase ^ 1);
+            const uint32_t st = smem_a + st_u * STAGE_BYTES;
+            if (issuer) {
+              if (PAIR) {
+                const uint32_t fb = full_c + 8 * st_u;
+                if (leader) mbar_arrive_expect_tx_a(full_a + 8 * st_u, 2 * STAGE_BYTES);   // bytes of both CTAs
+                tma_load_4d_2sm_a(st, &tm_xhi, fb, c0, w0 + kw, h0 + kh, img);
+                tma_load_4d_2sm_a(st + TC_A_BYTES, &tm_xlo, fb, c0, w0 + kw, h0 + kh, img);
+                tma_load_3d_2sm_a(st + 2 * TC_A_BYTES, &tm_whi, fb, c0, n0, tap);
+                tma_load_3d_2sm_a(st + 2 * TC_A_BYTES + B_BYTES, &tm_wlo, fb, c0, n0, tap);
+              } else {
+                const uint32_t fb = full_a + 8 * st_u;
+                mbar_arrive_expect_tx_a(fb, STAGE_BYTES);
+                tma_load_4d_a(st, &tm_xhi, fb, c0, w0 + kw, h0 + kh, img);
+                tma_load_4d_a(st + TC_A_BYTES, &tm_xlo, fb, c0, w0 + kw, h0 + kh, img);
+                tma_load_3d_a(st + 2 * TC_A_BYTES, &tm_whi, fb, c0, n0, tap);
+                tma_load_3d_a(st + 2 * TC_A_BYTES + B_BYTES, &tm_wlo, fb, c0, n0, tap);
+              }
+            }
+            __syncwarp();
+            if (++stage == STAGES) { stage = 0; phase ^= 1; }
           }
-          if (++stage == STAGES) { stage = 0; phase ^= 1; }
         }
-        }
-      }
       }
     }
   } else if (warp == 1) {
@@ -460,7 +540,7 @@ conv3x3_tc_kernel(const __grid_constant__ CUtensorMap tm_xhi, const __grid_const
               const uint32_t st = warp_uniform((uint32_t)stage);
               mbar_wait_warp_a(full_a + 8 * st, phase);
               tc_fence_after();
-              const uint32_t toff = (uint32_t)((tap / 3) * TC_HALO_W + tap % 3) * 128u;
+              const uint32_t toff = warp_uniform((uint32_t)((tap / 3) * TC_HALO_W + tap % 3) * 128u);
               const uint64_t a_hi = kHaloDesc | (uint64_t)(((ha + toff) >> 4) & 0x3fffu);
               const uint64_t a_lo = kHaloDesc | (uint64_t)(((ha + TC_HALO_PLANE + toff) >> 4) & 0x3fffu);
               const uint32_t sb = ring_a + st * STAGE_BYTES;

@@ -201,23 +201,34 @@ gemm2_f16_top16_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_co
   const int kiters = g.K / D1_BK;
 
   if (warp == 0) {
-    if (lane == 0) {
+    // TMA producer (both CTAs): convergent warp, lane 0 issues, warp-uniform operands (tc_conv.cu)
+    {
+      const bool issuer = lane == 0;
+      const uint32_t smem_a = warp_uniform(smem_u32(smem));
+      const uint32_t bars_a = smem_a + STAGES * STAGE;
+      const uint32_t full_a = bars_a, empty_a = bars_a + 8 * STAGES;
+      const uint32_t full_c = warp_uniform(mapa_u32(full_a, 0));   // the leader's barriers, shared::cluster addresses
+      const int rank_u = (int)warp_uniform(rank);
       int stage = 0; uint32_t phase = 0;
       for (int item = unit0; item < g.total_items; item += unit_stride) {
         int mp, nt0, ntn;
         decode(item, mp, nt0, ntn);
-        const int row0 = (mp * 2 + (int)rank) * 128;
+        const int row0 = (int)warp_uniform((uint32_t)((mp * 2 + rank_u) * 128));
         for (int nt = nt0; nt < nt0 + ntn; ++nt) {
-          const int col0 = nt * TILE_N + (int)rank * (D1_BN / 2);
+          const int col0 = (int)warp_uniform((uint32_t)(nt * TILE_N + rank_u * (D1_BN / 2)));
           for (int kit = 0; kit < kiters; ++kit) {
-            mbar_wait(&empty_bar[stage], phase ^ 1);
-            uint8_t* st = smem + stage * STAGE;
-            const uint32_t lead_full = mapa_u32(smem_u32(&full_bar[stage]), 0);
-            if (leader) mbar_arrive_expect_tx(&full_bar[stage], 2 * STAGE);   // bytes of BOTH CTAs; the peer only loads
-            tma_load_2d_2sm(st, &tm_a, lead_full, kit * D1_BK, row0);
+            const uint32_t sg = warp_uniform((uint32_t)stage);
+            mbar_wait_warp_a(empty_a + 8 * sg, phase ^ 1);
+            const uint32_t st = smem_a + sg * STAGE;
+            const int k0 = (int)warp_uniform((uint32_t)(kit * D1_BK));
+            if (issuer) {
+              if (leader) mbar_arrive_expect_tx_a(full_a + 8 * sg, 2 * STAGE);   // bytes of BOTH CTAs; the peer only loads
+              tma_load_2d_2sm_a(st, &tm_a, full_c + 8 * sg, k0, row0);
 #pragma unroll
-            for (int j = 0; j < SUB; ++j)     // rows beyond the matrix are zero-filled by the TMA unit
-              tma_load_2d_2sm(st + D1_A_BYTES + j * D1_BH_BYTES, &tm_b, lead_full, kit * D1_BK, col0 + j * D1_BN);
+              for (int j = 0; j < SUB; ++j)     // rows beyond the matrix are zero-filled by the TMA unit
+                tma_load_2d_2sm_a(st + D1_A_BYTES + j * D1_BH_BYTES, &tm_b, full_c + 8 * sg, k0, col0 + j * D1_BN);
+            }
+            __syncwarp();
             if (++stage == STAGES) { stage = 0; phase ^= 1; }
           }
         }

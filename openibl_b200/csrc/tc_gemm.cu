@@ -146,8 +146,15 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tm_ahi, const __grid_constant
       }
     }
   } else if (warp == 1) {
-    if (lane == 0) {
+    // MMA issuer: convergent warp, lane 0 issues, ring position and bases warp-uniform (tc_conv.cu explains why)
+    {
+      const bool issuer = lane == 0;
       constexpr uint32_t idesc = umma_idesc_bf16_f32(GT_BM, BN);
+      const uint32_t tmem_u = warp_uniform(tmem_base);
+      const uint32_t smem_a = warp_uniform(smem_u32(smem));
+      const uint32_t bars_a = smem_a + STAGES * STAGE_BYTES;
+      const uint32_t full_a = bars_a, empty_a = bars_a + 8 * STAGES;
+      const uint32_t tfull_a = bars_a + 16 * STAGES, tempty_a = tfull_a + 16;
       int stage = 0;
       uint32_t phase = 0;
       int it = 0;
@@ -155,31 +162,36 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tm_ahi, const __grid_constant
         int mt, nt0, ntn, k0, kn;
         decode(item, mt, nt0, ntn, k0, kn);
         for (int nt = nt0; nt < nt0 + ntn; ++nt, ++it) {
-          const int as = it & 1;
+          const uint32_t as = warp_uniform((uint32_t)(it & 1));
           const uint32_t aphase = (it >> 1) & 1;
-          mbar_wait(&tempty_bar[as], aphase ^ 1);
+          mbar_wait_warp_a(tempty_a + 8 * as, aphase ^ 1);
           tc_fence_after();
-          const uint32_t d_tmem = tmem_base + as * BN;
+          const uint32_t d_tmem = tmem_u + as * BN;
           for (int kit = 0; kit < kn; ++kit) {
-            mbar_wait(&full_bar[stage], phase);
+            const uint32_t sg = warp_uniform((uint32_t)stage);
+            mbar_wait_warp_a(full_a + 8 * sg, phase);
             tc_fence_after();
-            const uint32_t sa = smem_u32(smem + stage * STAGE_BYTES);
-            const uint64_t a_hi = umma_desc_kmajor<BK>(sa);
-            const uint64_t a_lo = umma_desc_kmajor<BK>(sa + A_BYTES);
-            const uint64_t b_hi = umma_desc_kmajor<BK>(sa + 2 * A_BYTES);
-            const uint64_t b_lo = umma_desc_kmajor<BK>(sa + 2 * A_BYTES + B_BYTES);
+            const uint32_t sa = smem_a + sg * STAGE_BYTES;
+            if (issuer) {
+              const uint64_t a_hi = umma_desc_kmajor<BK>(sa);
+              const uint64_t a_lo = umma_desc_kmajor<BK>(sa + A_BYTES);
+              const uint64_t b_hi = umma_desc_kmajor<BK>(sa + 2 * A_BYTES);
+              const uint64_t b_lo = umma_desc_kmajor<BK>(sa + 2 * A_BYTES + B_BYTES);
 #pragma unroll
-            for (int k = 0; k < BK / 16; ++k) {
-              const uint64_t ko = (uint64_t)(k * 2);
-              umma_bf16(d_tmem, a_lo + ko, b_hi + ko, idesc, (kit > 0 || k > 0) ? 1u : 0u);
-              umma_bf16(d_tmem, a_hi + ko, b_lo + ko, idesc, 1u);
-              umma_bf16(d_tmem, a_hi + ko, b_hi + ko, idesc, 1u);
+              for (int k = 0; k < BK / 16; ++k) {
+                const uint64_t ko = (uint64_t)(k * 2);
+                umma_bf16(d_tmem, a_lo + ko, b_hi + ko, idesc, (kit > 0 || k > 0) ? 1u : 0u);
+                umma_bf16(d_tmem, a_hi + ko, b_lo + ko, idesc, 1u);
+                umma_bf16(d_tmem, a_hi + ko, b_hi + ko, idesc, 1u);
+              }
+              if (MC) umma_commit_mc_a(empty_a + 8 * sg, 0x3);   // frees the slot in both CTAs of the pair
+              else umma_commit_a(empty_a + 8 * sg);
             }
-            if (MC) umma_commit_mc(&empty_bar[stage], 0x3);   // frees the slot in both CTAs of the pair
-            else umma_commit(&empty_bar[stage]);
+            __syncwarp();
             if (++stage == STAGES) { stage = 0; phase ^= 1; }
           }
-          umma_commit(&tfull_bar[as]);
+          if (issuer) umma_commit_a(tfull_a + 8 * as);
+          __syncwarp();
         }
       }
     }

@@ -328,7 +328,12 @@ netvlad_tc_kernel(const __grid_constant__ CUtensorMap tm_xhi, const __grid_const
   const int n_units = a.B * a.G;
 
   if (warp == 0) {
-    if (lane == 0) {
+    // TMA producer: same discipline as the MMA issuer below (convergent warp, lane 0 issues, warp-uniform operands)
+    {
+      const bool issuer = lane == 0;
+      const uint32_t smem_a = warp_uniform(smem_u32(smem));
+      const uint32_t bars_a = smem_a + NV_NSTAGE * NV_STAGE + 2 * NV_SLOT;
+      const uint32_t full_a = bars_a, empty_a = bars_a + 24;
       int stage = 0; uint32_t phase = 0;
       NvIter c1, c2;
       c1.init(blockIdx.x, gridDim.x, a.G, a.T, n_units);
@@ -336,39 +341,51 @@ netvlad_tc_kernel(const __grid_constant__ CUtensorMap tm_xhi, const __grid_const
       int n1 = 0, n2 = 0;
       while (c2.valid()) {
         if (c1.valid()) {                         // GEMM 1 stages: one 64-channel chunk + its W chunk
-          const int b = c1.u / a.G, p0 = c1.t * 128;
-          for (int c = 0; c < 8; ++c) {
-            const int cc = c;   // (a per-CTA rotated chunk order was tried against the slow first tile: no gain, and
-                                // it makes the fp32 summation order depend on the batch composition)
-            mbar_wait(&empty_bar[stage], phase ^ 1);
-            uint8_t* st = smem + stage * NV_STAGE;
-            mbar_arrive_expect_tx(&full_bar[stage], 3 * NV_SLOT);
-            tma_load_3d(st, &tm_xhi, &full_bar[stage], cc * 64, p0, b);
-            tma_load_3d(st + NV_SLOT, &tm_xlo, &full_bar[stage], cc * 64, p0, b);
-            tma_load_2d(st + 2 * NV_SLOT, &tm_whi, &full_bar[stage], cc * 64, 0);
-            tma_load_2d(st + 2 * NV_SLOT + 8192, &tm_wlo, &full_bar[stage], cc * 64, 0);
+          const int b = (int)warp_uniform((uint32_t)(c1.u / a.G)), p0 = (int)warp_uniform((uint32_t)(c1.t * 128));
+          for (int c = 0; c < 8; ++c) {           // (a per-CTA rotated chunk order was tried against the slow first
+                                                  // tile: no gain, and it makes the fp32 summation order depend on
+                                                  // the batch composition)
+            const uint32_t sg = warp_uniform((uint32_t)stage);
+            mbar_wait_warp_a(empty_a + 8 * sg, phase ^ 1);
+            const uint32_t st = smem_a + sg * NV_STAGE, fb = full_a + 8 * sg;
+            if (issuer) {
+              mbar_arrive_expect_tx_a(fb, 3 * NV_SLOT);
+              tma_load_3d_a(st, &tm_xhi, fb, c * 64, p0, b);
+              tma_load_3d_a(st + NV_SLOT, &tm_xlo, fb, c * 64, p0, b);
+              tma_load_2d_a(st + 2 * NV_SLOT, &tm_whi, fb, c * 64, 0);
+              tma_load_2d_a(st + 2 * NV_SLOT + 8192, &tm_wlo, fb, c * 64, 0);
+            }
+            __syncwarp();
             if (++stage == NV_NSTAGE) { stage = 0; phase ^= 1; }
           }
           c1.next();
           ++n1;
           if (c1.valid()) {                       // rolling L2 prefetch: the NEXT tile's boxes, behind this tile's
-            const int bn = c1.u / a.G;            // loads (prefetching the whole unit up front delayed the first
-            for (int c2i = 0; c2i < 8; ++c2i) {   // logits of every CTA to 10 us)
-              tma_prefetch_3d(&tm_xhi, c2i * 64, c1.t * 128, bn);
-              tma_prefetch_3d(&tm_xlo, c2i * 64, c1.t * 128, bn);
+            const int bn = (int)warp_uniform((uint32_t)(c1.u / a.G));   // loads (prefetching the whole unit up front
+            const int pn = (int)warp_uniform((uint32_t)(c1.t * 128));   // delayed the first logits of every CTA to 10 us)
+            if (issuer) {
+              for (int c2i = 0; c2i < 8; ++c2i) {
+                tma_prefetch_3d(&tm_xhi, c2i * 64, pn, bn);
+                tma_prefetch_3d(&tm_xlo, c2i * 64, pn, bn);
+              }
             }
+            __syncwarp();
           }
         }
         if (n2 < n1 - 1 || !c1.valid()) {         // GEMM 2 stages: one 128-channel block (L2 hits)
-          const int b = c2.u / a.G, p0 = c2.t * 128;
+          const int b = (int)warp_uniform((uint32_t)(c2.u / a.G)), p0 = (int)warp_uniform((uint32_t)(c2.t * 128));
           for (int cb = 0; cb < 4; ++cb) {
-            mbar_wait(&empty_bar[stage], phase ^ 1);
-            uint8_t* st = smem + stage * NV_STAGE;
-            mbar_arrive_expect_tx(&full_bar[stage], 4 * NV_SLOT);
-            tma_load_3d(st, &tm_xhi, &full_bar[stage], cb * 128, p0, b);
-            tma_load_3d(st + NV_SLOT, &tm_xhi, &full_bar[stage], cb * 128 + 64, p0, b);
-            tma_load_3d(st + 2 * NV_SLOT, &tm_xlo, &full_bar[stage], cb * 128, p0, b);
-            tma_load_3d(st + 3 * NV_SLOT, &tm_xlo, &full_bar[stage], cb * 128 + 64, p0, b);
+            const uint32_t sg = warp_uniform((uint32_t)stage);
+            mbar_wait_warp_a(empty_a + 8 * sg, phase ^ 1);
+            const uint32_t st = smem_a + sg * NV_STAGE, fb = full_a + 8 * sg;
+            if (issuer) {
+              mbar_arrive_expect_tx_a(fb, 4 * NV_SLOT);
+              tma_load_3d_a(st, &tm_xhi, fb, cb * 128, p0, b);
+              tma_load_3d_a(st + NV_SLOT, &tm_xhi, fb, cb * 128 + 64, p0, b);
+              tma_load_3d_a(st + 2 * NV_SLOT, &tm_xlo, fb, cb * 128, p0, b);
+              tma_load_3d_a(st + 3 * NV_SLOT, &tm_xlo, fb, cb * 128 + 64, p0, b);
+            }
+            __syncwarp();
             if (++stage == NV_NSTAGE) { stage = 0; phase ^= 1; }
           }
           c2.next();
@@ -377,10 +394,23 @@ netvlad_tc_kernel(const __grid_constant__ CUtensorMap tm_xhi, const __grid_const
       }
     }
   } else if (warp == 1) {
-    if (lane == 0) {
+    // MMA issuer: the whole warp walks the schedule in convergent code, lane 0 issues; ring position and bases pass
+    // through warp_uniform() so that every tcgen05 operand lives in a uniform register.  Inside an `if (lane == 0)`
+    // region each of the 160 small MMAs of a tile (N = 64 / 128: 32-65 clk of tensor pipe) was wrapped in an ELECT +
+    // R2UR.BROADCAST loop of ~90-100 clk -- round 1's "3.5 us + 4.7 us per tile" were ISSUE time, not shared-memory
+    // bandwidth.
+    {
+      const bool issuer = lane == 0;
       constexpr uint32_t idesc_n128 = umma_idesc_bf16_f32(128, 128);
       constexpr uint32_t idesc_n64 = umma_idesc_bf16_f32(128, 64);
       constexpr uint32_t idesc2 = umma_idesc_bf16_f32_mn(128, 64, 1, 1);
+      const uint32_t tmem_u = warp_uniform(tmem_base);
+      const uint32_t smem_a = warp_uniform(smem_u32(smem));
+      const uint32_t ah = smem_a + NV_NSTAGE * NV_STAGE, al = ah + NV_SLOT;
+      const uint32_t bars_a = al + NV_SLOT;
+      const uint32_t full_a = bars_a, empty_a = bars_a + 24, zfull_a = bars_a + 48, zempty_a = bars_a + 64;
+      const uint32_t afull_a = bars_a + 80, aempty_a = bars_a + 88, dfull_a = bars_a + 96, dempty_a = bars_a + 104;
+      const uint32_t t_du = tmem_u + 256;
       int stage = 0; uint32_t phase = 0;
       NvIter c1, c2;
       c1.init(blockIdx.x, gridDim.x, a.G, a.T, n_units);
@@ -389,59 +419,71 @@ netvlad_tc_kernel(const __grid_constant__ CUtensorMap tm_xhi, const __grid_const
       while (c2.valid()) {
         if (c1.valid()) {
           // ---- GEMM 1 of tile n1: Z[128 px, (x.W_hi) | (x_hi.W_lo)] ----
-          const int zb = n1 & 1;
-          mbar_wait(&z_empty[zb], ((n1 >> 1) & 1) ^ 1);
+          const uint32_t zb = warp_uniform((uint32_t)(n1 & 1));
+          mbar_wait_warp_a(zempty_a + 8 * zb, ((n1 >> 1) & 1) ^ 1);
           tc_fence_after();
-          const uint32_t t_z = tmem_base + zb * 128;
+          const uint32_t t_z = tmem_u + zb * 128;
           for (int c = 0; c < 8; ++c) {
-            mbar_wait(&full_bar[stage], phase);
+            const uint32_t st = warp_uniform((uint32_t)stage);
+            mbar_wait_warp_a(full_a + 8 * st, phase);
             tc_fence_after();
-            const uint32_t sa = smem_u32(smem + stage * NV_STAGE);
-            const uint64_t xh = umma_desc_kmajor_sw128(sa), xl = umma_desc_kmajor_sw128(sa + NV_SLOT);
-            const uint64_t wcat = umma_desc_kmajor_sw128(sa + 2 * NV_SLOT);   // 128 rows: W_hi then W_lo
+            const uint32_t sa = smem_a + st * NV_STAGE;
+            if (issuer) {
+              const uint64_t xh = umma_desc_kmajor_sw128(sa), xl = umma_desc_kmajor_sw128(sa + NV_SLOT);
+              const uint64_t wcat = umma_desc_kmajor_sw128(sa + 2 * NV_SLOT);   // 128 rows: W_hi then W_lo
 #pragma unroll
-            for (int k = 0; k < 4; ++k) {
-              const uint64_t ko = (uint64_t)(k * 2);
-              umma_bf16(t_z, xh + ko, wcat + ko, idesc_n128, (c > 0 || k > 0) ? 1u : 0u);
-              umma_bf16(t_z, xl + ko, wcat + ko, idesc_n64, 1u);               // x_lo . W_hi into columns 0-63
+              for (int k = 0; k < 4; ++k) {
+                const uint64_t ko = (uint64_t)(k * 2);
+                umma_bf16(t_z, xh + ko, wcat + ko, idesc_n128, (c > 0 || k > 0) ? 1u : 0u);
+                umma_bf16(t_z, xl + ko, wcat + ko, idesc_n64, 1u);               // x_lo . W_hi into columns 0-63
+              }
+              umma_commit_a(empty_a + 8 * st);
             }
-            umma_commit(&empty_bar[stage]);
+            __syncwarp();
             if (++stage == NV_NSTAGE) { stage = 0; phase ^= 1; }
           }
-          umma_commit(&z_full[zb]);
+          if (issuer) umma_commit_a(zfull_a + 8 * zb);
+          __syncwarp();
           c1.next();
           ++n1;
         }
         if (n2 < n1 - 1 || !c1.valid()) {
           // ---- GEMM 2 of tile n2: V[128 c, 64 k] (4 channel blocks) += X^T a' ----
-          if (c2.first()) {
-            mbar_wait(d_empty, (c2.useq & 1) ^ 1);   // the previous unit's partial has been read out of TMEM
+          const bool fresh = c2.first();
+          if (fresh) {
+            mbar_wait_warp_a(dempty_a, (c2.useq & 1) ^ 1);   // the previous unit's partial has been read out of TMEM
             tc_fence_after();
           }
-          mbar_wait(a_full, n2 & 1);
+          mbar_wait_warp_a(afull_a, n2 & 1);
           tc_fence_after();
-          const uint32_t ah = smem_u32(asm_hi), al = smem_u32(asm_lo);
           for (int cb = 0; cb < 4; ++cb) {
-            mbar_wait(&full_bar[stage], phase);
+            const uint32_t st = warp_uniform((uint32_t)stage);
+            mbar_wait_warp_a(full_a + 8 * st, phase);
             tc_fence_after();
-            const uint32_t sa = smem_u32(smem + stage * NV_STAGE);
+            const uint32_t sa = smem_a + st * NV_STAGE;
+            const uint32_t d = t_du + warp_uniform((uint32_t)cb) * 64;
+            if (issuer) {
 #pragma unroll
-            for (int ks = 0; ks < 8; ++ks) {     // 16 pixel rows (2048 B) per MMA
-              const uint32_t off = ks * 2048;
-              const uint64_t xh = umma_desc_mnmajor_sw128(sa + off, NV_SLOT);
-              const uint64_t xl = umma_desc_mnmajor_sw128(sa + 2 * NV_SLOT + off, NV_SLOT);
-              const uint64_t bh = umma_desc_mnmajor_sw128(ah + off, 0);
-              const uint64_t bl = umma_desc_mnmajor_sw128(al + off, 0);
-              const uint32_t d = t_d + cb * 64;
-              umma_bf16(d, xl, bh, idesc2, (c2.first() && ks == 0) ? 0u : 1u);
-              umma_bf16(d, xh, bl, idesc2, 1u);
-              umma_bf16(d, xh, bh, idesc2, 1u);
+              for (int ks = 0; ks < 8; ++ks) {     // 16 pixel rows (2048 B) per MMA
+                const uint32_t off = ks * 2048;
+                const uint64_t xh = umma_desc_mnmajor_sw128(sa + off, NV_SLOT);
+                const uint64_t xl = umma_desc_mnmajor_sw128(sa + 2 * NV_SLOT + off, NV_SLOT);
+                const uint64_t bh = umma_desc_mnmajor_sw128(ah + off, 0);
+                const uint64_t bl = umma_desc_mnmajor_sw128(al + off, 0);
+                umma_bf16(d, xl, bh, idesc2, (fresh && ks == 0) ? 0u : 1u);
+                umma_bf16(d, xh, bl, idesc2, 1u);
+                umma_bf16(d, xh, bh, idesc2, 1u);
+              }
+              umma_commit_a(empty_a + 8 * st);
             }
-            umma_commit(&empty_bar[stage]);
+            __syncwarp();
             if (++stage == NV_NSTAGE) { stage = 0; phase ^= 1; }
           }
-          umma_commit(a_empty);                  // a' may be overwritten
-          if (c2.last()) umma_commit(d_full);
+          if (issuer) {
+            umma_commit_a(aempty_a);               // a' may be overwritten
+            if (c2.last()) umma_commit_a(dfull_a);
+          }
+          __syncwarp();
           c2.next();
           ++n2;
         }
