@@ -18,6 +18,23 @@ __device__ __forceinline__ uint32_t smem_u32(const void* p) {
 // an ELECT / R2UR.BROADCAST loop.
 __device__ __forceinline__ uint32_t warp_uniform(uint32_t v) { return __reduce_or_sync(0xffffffffu, v); }
 
+// One lane of the converged warp (elect.sync).  ptxas knows that exactly one thread runs the guarded block and emits the
+// tcgen05 / TMA instructions inside it back to back; behind `if (lane == 0)` it cannot know, and wraps EVERY such
+// instruction in an ELECT / PLOP3 / BRA.U.ANY loop over the "possibly several" active threads -- ~90 clk of dependent
+// issue per MMA (ncu source view), more than an N <= 128 MMA occupies the tensor pipe.  A tcgen05.commit tracks the
+// MMAs of the executing thread: keep a commit in the same elected block as the MMAs it covers.
+__device__ __forceinline__ bool elect_one() {
+  uint32_t pred;
+  asm volatile(
+      "{\n\t"
+      ".reg .pred p;\n\t"
+      "elect.sync _|p, 0xffffffff;\n\t"
+      "selp.u32 %0, 1, 0, p;\n\t"
+      "}"
+      : "=r"(pred));
+  return pred != 0;
+}
+
 // ---- mbarrier -------------------------------------------------------------------------------
 __device__ __forceinline__ void mbar_init(uint64_t* bar, uint32_t count) {
   asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count) : "memory");

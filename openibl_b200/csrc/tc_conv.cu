@@ -342,9 +342,8 @@ conv3x3_tc_kernel(const __grid_constant__ CUtensorMap tm_xhi, const __grid_const
 
   if (warp == 0) {
     // ================= TMA producer =================
-    // same discipline as the MMA issuer below: convergent warp, lane 0 issues, ring positions / coordinates warp-uniform
+    // same discipline as the MMA issuer below: convergent warp, one elected lane issues, ring positions / coordinates warp-uniform
     {
-      const bool issuer = lane == 0;
       const uint32_t smem_a = warp_uniform(smem_u32(smem));
       const uint32_t ring_a = smem_a + A_RING;
       const uint32_t bars_a = ring_a + STAGES * STAGE_BYTES;
@@ -372,7 +371,7 @@ conv3x3_tc_kernel(const __grid_constant__ CUtensorMap tm_xhi, const __grid_const
       // lane 0 polls once; the answer is broadcast so that the branch on it is warp-uniform
       auto try_wait_warp = [&](uint32_t bar, uint32_t parity) -> bool {
         uint32_t ok = 0;
-        if (issuer) {
+        if (lane == 0) {
           asm volatile(
               "{\n\t"
               ".reg .pred p;\n\t"
@@ -400,7 +399,7 @@ conv3x3_tc_kernel(const __grid_constant__ CUtensorMap tm_xhi, const __grid_const
             const int c0 = (int)warp_uniform((uint32_t)(kcA * TC_BK));
             const uint32_t sa = smem_a + as_u * TC_HALO_STAGE;
             constexpr uint32_t kHaloBytes = 2u * TC_HALO_W * TC_HALO_H * 128u;
-            if (issuer) {
+            if (elect_one()) {
               if (PAIR) {
                 if (leader) mbar_arrive_expect_tx_a(afull_a + 8 * as_u, 2 * kHaloBytes);
                 tma_load_4d_2sm_a(sa, &tm_xhi, afull_c + 8 * as_u, c0, w0 - 1, h0 - 1, img);
@@ -423,7 +422,7 @@ conv3x3_tc_kernel(const __grid_constant__ CUtensorMap tm_xhi, const __grid_const
             const int c0 = (int)warp_uniform((uint32_t)(kcB * TC_BK));
             const int tap = (int)warp_uniform((uint32_t)tapB);
             const uint32_t st = ring_a + st_u * STAGE_BYTES;
-            if (issuer) {
+            if (elect_one()) {
               if (PAIR) {
                 if (leader) mbar_arrive_expect_tx_a(full_a + 8 * st_u, 2 * STAGE_BYTES);
                 tma_load_3d_2sm_a(st, &tm_whi, full_c + 8 * st_u, c0, n0, tap);
@@ -450,7 +449,7 @@ conv3x3_tc_kernel(const __grid_constant__ CUtensorMap tm_xhi, const __grid_const
             const uint32_t st_u = warp_uniform((uint32_t)stage);
             mbar_wait_warp_a(empty_a + 8 * st_u, phase ^ 1);
             const uint32_t st = smem_a + st_u * STAGE_BYTES;
-            if (issuer) {
+            if (elect_one()) {
               if (PAIR) {
                 const uint32_t fb = full_c + 8 * st_u;
                 if (leader) mbar_arrive_expect_tx_a(full_a + 8 * st_u, 2 * STAGE_BYTES);   // bytes of both CTAs
@@ -475,14 +474,15 @@ conv3x3_tc_kernel(const __grid_constant__ CUtensorMap tm_xhi, const __grid_const
     }
   } else if (warp == 1) {
     // ================= MMA issuer =================
-    // The whole warp walks the schedule in convergent code and lane 0 alone executes the tcgen05 instructions; the ring
-    // position, the TMEM base and the shared-memory base pass through a REDUX (warp_uniform) once per stage, so every
-    // MMA operand and barrier address lives in a uniform register.  With the loop inside `if (lane == 0)` the compiler
-    // treated descriptors and TMEM addresses as per-thread values and wrapped EACH MMA in an ELECT + 5 x
-    // R2UR.BROADCAST loop: ~90 clk of dependent issue per MMA (ncu source view of the fused conv1 kernel), more than an
-    // N <= 128 MMA occupies the tensor pipe.
+    // The whole warp walks the schedule in convergent code; ONE ELECTED lane (elect.sync) executes the tcgen05
+    // instructions of a stage, and the ring position, TMEM base and shared-memory base pass through a REDUX
+    // (warp_uniform) once per stage, so every operand lives in a uniform register.  With the loop inside
+    // `if (lane == 0)` ptxas (a) treated descriptors and TMEM addresses as per-thread values (5 R2UR.BROADCASTs per MMA)
+    // and (b) wrapped EACH MMA in an ELECT / PLOP3 / BRA.U.ANY loop over the possibly-several active threads: ~90 clk of
+    // dependent issue per MMA (ncu source view of the fused conv1 kernel: the issuing thread was busy 75 % of the time
+    // with the tensor pipe 40 % active), more than an N <= 128 MMA occupies the tensor pipe.  Behind elect.sync the
+    // MMAs of a stage are consecutive UTCHMMA instructions.
     if (warp_uniform(leader ? 1u : 0u)) {
-      const bool issuer = lane == 0;
       const uint32_t tmem_u = warp_uniform(tmem_base);
       const uint32_t smem_a = warp_uniform(smem_u32(smem));
       const uint32_t ring_a = smem_a + A_RING;
@@ -544,16 +544,18 @@ conv3x3_tc_kernel(const __grid_constant__ CUtensorMap tm_xhi, const __grid_const
               const uint64_t a_hi = kHaloDesc | (uint64_t)(((ha + toff) >> 4) & 0x3fffu);
               const uint64_t a_lo = kHaloDesc | (uint64_t)(((ha + TC_HALO_PLANE + toff) >> 4) & 0x3fffu);
               const uint32_t sb = ring_a + st * STAGE_BYTES;
-              if (issuer) {
+              if (elect_one()) {
                 mma_step(d_tmem, a_hi, a_lo, umma_desc_kmajor_sw128(sb), umma_desc_kmajor_sw128(sb + B_BYTES),
                          kc == 0 && tap == 0);
                 commit(empty_a + 8 * st);           // frees the weight slot (in both CTAs of a pair) when these MMAs retire
+                if (tap == 8) {
+                  commit(aempty_a + 8 * hs);        // ... the halo slot after its ninth tap
+                  if (kc == kchunks - 1) commit(tfull_a + 8 * as);   // ... and hands the accumulator to the epilogue
+                }
               }
               __syncwarp();
               if (++stage == STAGES) { stage = 0; phase ^= 1; }
             }
-            if (issuer) commit(aempty_a + 8 * hs);
-            __syncwarp();
             if (++hstage == NA) { hstage = 0; hphase ^= 1; }
           }
         } else {
@@ -562,18 +564,17 @@ conv3x3_tc_kernel(const __grid_constant__ CUtensorMap tm_xhi, const __grid_const
             mbar_wait_warp_a(full_a + 8 * st, phase);
             tc_fence_after();
             const uint32_t sa = smem_a + st * STAGE_BYTES;
-            if (issuer) {
+            if (elect_one()) {
               mma_step(d_tmem, umma_desc_kmajor_sw128(sa), umma_desc_kmajor_sw128(sa + TC_A_BYTES),
                        umma_desc_kmajor_sw128(sa + 2 * TC_A_BYTES), umma_desc_kmajor_sw128(sa + 2 * TC_A_BYTES + B_BYTES),
                        kit == 0);
               commit(empty_a + 8 * st);             // frees the smem slot (in both CTAs of a pair) when these MMAs retire
+              if (kit == kiters - 1) commit(tfull_a + 8 * as);   // accumulator ready for the epilogue
             }
             __syncwarp();
             if (++stage == STAGES) { stage = 0; phase ^= 1; }
           }
         }
-        if (issuer) commit(tfull_a + 8 * as);       // accumulator ready for the epilogue
-        __syncwarp();
       }
     }
   } else {
@@ -875,30 +876,30 @@ conv1_fused_tc_kernel(const __grid_constant__ CUtensorMap tm_whi, const __grid_c
   const long long HW = (long long)a.H * a.W;
 
   if (warp == 0) {
-    // ================= TMA producer: conv1_2 weight taps =================
-    if (lane == 0) {
+    // ================= TMA producer: conv1_2 weight taps (convergent warp, one elected lane issues) =================
+    {
       int stage = 0; uint32_t phase = 0;
       for (int tile = blockIdx.x; tile < a.total_tiles; tile += gridDim.x) {
         for (int tap = 0; tap < 9; ++tap) {
-          mbar_wait(&w_empty[stage], phase ^ 1);
+          mbar_wait_warp(&w_empty[stage], phase ^ 1);
           uint8_t* st = w2 + stage * F1_W2_STAGE;
-          mbar_arrive_expect_tx(&w_full[stage], F1_W2_STAGE);
-          tma_load_3d(st, &tm_whi, &w_full[stage], 0, 0, tap);
-          tma_load_3d(st + F1_W2_STAGE / 2, &tm_wlo, &w_full[stage], 0, 0, tap);
+          if (elect_one()) {
+            mbar_arrive_expect_tx(&w_full[stage], F1_W2_STAGE);
+            tma_load_3d(st, &tm_whi, &w_full[stage], 0, 0, tap);
+            tma_load_3d(st + F1_W2_STAGE / 2, &tm_wlo, &w_full[stage], 0, 0, tap);
+          }
+          __syncwarp();
           if (++stage == F1_W2_STAGES) { stage = 0; phase ^= 1; }
         }
       }
     }
   } else if (warp == 1) {
     // ================= MMA issuer =================
-    // The WHOLE warp walks the schedule (waits included) and lane 0 alone executes the tcgen05 instructions: every
-    // operand is then computed in convergent code from warp-uniform values and lives in uniform registers.  With the
-    // loop inside `if (lane == 0)` the compiler treated tmem addresses and descriptors as per-thread values and wrapped
-    // each MMA in an ELECT / R2UR.BROADCAST "waterfall" loop: ~90 clk of dependent issue per MMA (ncu source view),
-    // more than the 32-65 clk an N = 64 / 128 MMA occupies the tensor pipe -- the kernel was issue-bound at 40 %
-    // tensor-pipe activity.
+    // The whole warp walks the schedule in convergent code and ONE ELECTED lane executes the tcgen05 instructions of a
+    // stage (see conv3x3_tc_kernel's issuer): 72 + 12 small MMAs per tile (N = 64 / 128: 32-65 clk of tensor pipe each)
+    // cost ~90 clk of issue apiece behind `if (lane == 0)` -- the kernel ran at 40 % tensor-pipe activity with the
+    // issuing thread busy 75 % of the time.
     {
-      const bool issuer = lane == 0;
       constexpr uint32_t idesc64 = umma_idesc_bf16_f32(TC_BM, 64);
       constexpr uint32_t idesc128 = umma_idesc_bf16_f32(TC_BM, 128);
       constexpr uint64_t kHaloDesc = ((uint64_t)1 << 16) | ((uint64_t)((TC_HALO_W * 128) >> 4) << 32) |
@@ -907,25 +908,23 @@ conv1_fused_tc_kernel(const __grid_constant__ CUtensorMap tm_whi, const __grid_c
       int n_tiles = 0;
       for (int tile = blockIdx.x; tile < a.total_tiles; tile += gridDim.x) ++n_tiles;
       auto issue_c1 = [&](int it) {
-        mbar_wait(a1_full, it & 1);
-        mbar_wait(acc1_empty, (it & 1) ^ 1);
+        mbar_wait_warp(a1_full, it & 1);
+        mbar_wait_warp(acc1_empty, (it & 1) ^ 1);
         tc_fence_after();
+        if (elect_one()) {
 #pragma unroll
-        for (int mt = 0; mt < 2; ++mt) {
-          const uint32_t sa = smem_u32(a1) + mt * 16384;
-          const uint64_t ah = umma_desc_kmajor_sw128(sa), al = umma_desc_kmajor_sw128(sa + F1_A1_PLANE);
-          const uint32_t d = t_acc1 + mt * 64;
+          for (int mt = 0; mt < 2; ++mt) {
+            const uint32_t sa = smem_u32(a1) + mt * 16384;
+            const uint64_t ah = umma_desc_kmajor_sw128(sa), al = umma_desc_kmajor_sw128(sa + F1_A1_PLANE);
+            const uint32_t d = t_acc1 + mt * 64;
 #pragma unroll
-          for (int k = 0; k < 2; ++k) {               // K = 32: two 16-wide steps
-            const uint64_t ko = (uint64_t)(k * 2);
-            if (issuer) {
+            for (int k = 0; k < 2; ++k) {               // K = 32: two 16-wide steps
+              const uint64_t ko = (uint64_t)(k * 2);
               umma_bf16(d, al + ko, b1h + ko, idesc64, k > 0 ? 1u : 0u);
               umma_bf16(d, ah + ko, b1l + ko, idesc64, 1u);
               umma_bf16(d, ah + ko, b1h + ko, idesc64, 1u);
             }
           }
-        }
-        if (issuer) {
           umma_commit(a1_empty);
           umma_commit(acc1_full);
         }
@@ -937,20 +936,20 @@ conv1_fused_tc_kernel(const __grid_constant__ CUtensorMap tm_whi, const __grid_c
         if (it + 1 < n_tiles) issue_c1(it + 1);
         const int hb = it & 1;
         const uint32_t hph = (it >> 1) & 1;
-        mbar_wait(&acc2_empty[hb], hph ^ 1);
-        mbar_wait(&halo_full[hb], hph);
+        mbar_wait_warp(&acc2_empty[hb], hph ^ 1);
+        mbar_wait_warp(&halo_full[hb], hph);
         tc_fence_after();
         const uint32_t d_tmem = tmem_base + hb * ACC2_COLS;
         const uint32_t ha = smem_u32(halo + hb * TC_HALO_STAGE);
         for (int tap = 0; tap < 9; ++tap) {
-          mbar_wait(&w_full[stage], phase);
+          mbar_wait_warp(&w_full[stage], phase);
           tc_fence_after();
           const uint32_t toff = (uint32_t)((tap / 3) * TC_HALO_W + tap % 3) * 128u;
           const uint64_t a_hi = kHaloDesc | (uint64_t)(((ha + toff) >> 4) & 0x3fffu);
           const uint64_t a_lo = kHaloDesc | (uint64_t)(((ha + TC_HALO_PLANE + toff) >> 4) & 0x3fffu);
           const uint32_t sb = smem_u32(w2 + stage * F1_W2_STAGE);
           const uint64_t b_cat = umma_desc_kmajor_sw128(sb);          // 128 rows: W_hi then W_lo
-          if (issuer) {
+          if (elect_one()) {
 #pragma unroll
             for (int k = 0; k < TC_BK / 16; ++k) {
               const uint64_t ko = (uint64_t)(k * 2);
@@ -959,15 +958,14 @@ conv1_fused_tc_kernel(const __grid_constant__ CUtensorMap tm_whi, const __grid_c
               umma_bf16(d_tmem + 128, a_lo + ko, b_cat + ko, idesc64, first);       // lo.hi
             }
             umma_commit(&w_empty[stage]);
+            if (tap == 8) {                           // same elected thread as the MMAs these commits cover
+              umma_commit(&halo_empty[hb]);
+              umma_commit(&acc2_full[hb]);
+            }
           }
           __syncwarp();
           if (++stage == F1_W2_STAGES) { stage = 0; phase ^= 1; }
         }
-        if (issuer) {
-          umma_commit(&halo_empty[hb]);
-          umma_commit(&acc2_full[hb]);
-        }
-        __syncwarp();
       }
     }
   } else if (warp <= 5) {

@@ -190,38 +190,49 @@ conv_wgrad_tc_kernel(const __grid_constant__ CUtensorMap tm_ghi, const __grid_co
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
 
+  // Producer and MMA issuer: the whole warp walks the loop in convergent code and ONE ELECTED lane (elect.sync) issues a
+  // stage's TMA / tcgen05 instructions, with ring position and addresses made warp-uniform -- see the MMA issuer of
+  // conv3x3_tc_kernel (tc_conv.cu) for what `if (lane == 0)` costs per instruction.
   if (warp == 0) {
-    if (lane == 0) {
-      int stage = 0; uint32_t phase = 0;
-      const int per_img = a.tiles_h * a.tiles_w;
-      for (long long b = b0; b < b1; ++b) {
-        const int n = (int)(b / per_img);
-        const int r = (int)(b - (long long)n * per_img);
-        const int h0 = (r / a.tiles_w) * 4, w0 = (r % a.tiles_w) * 16;
-        mbar_wait(&empty_bar[stage], phase ^ 1);
-        uint8_t* st = smem + stage * WG_STAGE;
-        mbar_arrive_expect_tx(&full_bar[stage], WG_STAGE);
-        const int co0 = mt * 128, ci0 = nt * 128;
-        tma_load_4d(st + 0 * WG_BOX, &tm_ghi, &full_bar[stage], co0, w0, h0, n);
-        tma_load_4d(st + 1 * WG_BOX, &tm_ghi, &full_bar[stage], co0 + 64, w0, h0, n);
-        tma_load_4d(st + 2 * WG_BOX, &tm_glo, &full_bar[stage], co0, w0, h0, n);
-        tma_load_4d(st + 3 * WG_BOX, &tm_glo, &full_bar[stage], co0 + 64, w0, h0, n);
-        tma_load_4d(st + 4 * WG_BOX, &tm_xhi, &full_bar[stage], ci0, w0 + kw - 1, h0 + kh - 1, n);
-        tma_load_4d(st + 5 * WG_BOX, &tm_xhi, &full_bar[stage], ci0 + 64, w0 + kw - 1, h0 + kh - 1, n);
-        tma_load_4d(st + 6 * WG_BOX, &tm_xlo, &full_bar[stage], ci0, w0 + kw - 1, h0 + kh - 1, n);
-        tma_load_4d(st + 7 * WG_BOX, &tm_xlo, &full_bar[stage], ci0 + 64, w0 + kw - 1, h0 + kh - 1, n);
-        if (++stage == WG_STAGES) { stage = 0; phase ^= 1; }
+    const uint32_t smem_a = warp_uniform(smem_u32(smem));
+    const uint32_t full_a = smem_a + WG_STAGES * WG_STAGE, empty_a = full_a + 8 * WG_STAGES;
+    int stage = 0; uint32_t phase = 0;
+    const int per_img = a.tiles_h * a.tiles_w;
+    const int co0 = mt * 128, ci0 = nt * 128;
+    for (long long b = b0; b < b1; ++b) {
+      const int n = (int)(b / per_img);
+      const int r = (int)(b - (long long)n * per_img);
+      const int nu = (int)warp_uniform((uint32_t)n);
+      const int h0 = (int)warp_uniform((uint32_t)((r / a.tiles_w) * 4)), w0 = (int)warp_uniform((uint32_t)((r % a.tiles_w) * 16));
+      const uint32_t sg = warp_uniform((uint32_t)stage);
+      mbar_wait_warp_a(empty_a + 8 * sg, phase ^ 1);
+      const uint32_t st = smem_a + sg * WG_STAGE, fb = full_a + 8 * sg;
+      if (elect_one()) {
+        mbar_arrive_expect_tx_a(fb, WG_STAGE);
+        tma_load_4d_a(st + 0 * WG_BOX, &tm_ghi, fb, co0, w0, h0, nu);
+        tma_load_4d_a(st + 1 * WG_BOX, &tm_ghi, fb, co0 + 64, w0, h0, nu);
+        tma_load_4d_a(st + 2 * WG_BOX, &tm_glo, fb, co0, w0, h0, nu);
+        tma_load_4d_a(st + 3 * WG_BOX, &tm_glo, fb, co0 + 64, w0, h0, nu);
+        tma_load_4d_a(st + 4 * WG_BOX, &tm_xhi, fb, ci0, w0 + kw - 1, h0 + kh - 1, nu);
+        tma_load_4d_a(st + 5 * WG_BOX, &tm_xhi, fb, ci0 + 64, w0 + kw - 1, h0 + kh - 1, nu);
+        tma_load_4d_a(st + 6 * WG_BOX, &tm_xlo, fb, ci0, w0 + kw - 1, h0 + kh - 1, nu);
+        tma_load_4d_a(st + 7 * WG_BOX, &tm_xlo, fb, ci0 + 64, w0 + kw - 1, h0 + kh - 1, nu);
       }
+      __syncwarp();
+      if (++stage == WG_STAGES) { stage = 0; phase ^= 1; }
     }
   } else if (warp == 1) {
-    if (lane == 0) {
-      constexpr uint32_t idesc = bwd_idesc_mn(128, 128);
-      int stage = 0; uint32_t phase = 0;
-      bool first = true;
-      for (long long b = b0; b < b1; ++b) {
-        mbar_wait(&full_bar[stage], phase);
-        tc_fence_after();
-        const uint32_t sa = smem_u32(smem + stage * WG_STAGE);
+    constexpr uint32_t idesc = bwd_idesc_mn(128, 128);
+    const uint32_t tmem_u = warp_uniform(tmem_base);
+    const uint32_t smem_a = warp_uniform(smem_u32(smem));
+    const uint32_t full_a = smem_a + WG_STAGES * WG_STAGE, empty_a = full_a + 8 * WG_STAGES, dfull_a = full_a + 16 * WG_STAGES;
+    int stage = 0; uint32_t phase = 0;
+    for (long long b = b0; b < b1; ++b) {
+      const uint32_t sg = warp_uniform((uint32_t)stage);
+      mbar_wait_warp_a(full_a + 8 * sg, phase);
+      tc_fence_after();
+      const uint32_t sa = smem_a + sg * WG_STAGE;
+      if (elect_one()) {
 #pragma unroll
         for (int ks = 0; ks < 4; ++ks) {          // 16 pixel rows (2048 B) per MMA
           const uint32_t off = ks * 2048;
@@ -229,15 +240,15 @@ conv_wgrad_tc_kernel(const __grid_constant__ CUtensorMap tm_ghi, const __grid_co
           const uint64_t gl = bwd_desc_mnmajor_sw128(sa + 2 * WG_BOX + off, WG_BOX);
           const uint64_t xh = bwd_desc_mnmajor_sw128(sa + 4 * WG_BOX + off, WG_BOX);
           const uint64_t xl = bwd_desc_mnmajor_sw128(sa + 6 * WG_BOX + off, WG_BOX);
-          umma_bf16(tmem_base, gl, xh, idesc, (first && ks == 0) ? 0u : 1u);
-          umma_bf16(tmem_base, gh, xl, idesc, 1u);
-          umma_bf16(tmem_base, gh, xh, idesc, 1u);
+          umma_bf16(tmem_u, gl, xh, idesc, (b == b0 && ks == 0) ? 0u : 1u);
+          umma_bf16(tmem_u, gh, xl, idesc, 1u);
+          umma_bf16(tmem_u, gh, xh, idesc, 1u);
         }
-        first = false;
-        umma_commit(&empty_bar[stage]);
-        if (++stage == WG_STAGES) { stage = 0; phase ^= 1; }
+        umma_commit_a(empty_a + 8 * sg);
+        if (b == b1 - 1) umma_commit_a(dfull_a);   // same elected thread as the MMAs it covers
       }
-      umma_commit(d_full);
+      __syncwarp();
+      if (++stage == WG_STAGES) { stage = 0; phase ^= 1; }
     }
   } else {
     const int q = warp & 3;

@@ -201,9 +201,8 @@ gemm2_f16_top16_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_co
   const int kiters = g.K / D1_BK;
 
   if (warp == 0) {
-    // TMA producer (both CTAs): convergent warp, lane 0 issues, warp-uniform operands (tc_conv.cu)
+    // TMA producer (both CTAs): convergent warp, one elected lane issues, warp-uniform operands (tc_conv.cu)
     {
-      const bool issuer = lane == 0;
       const uint32_t smem_a = warp_uniform(smem_u32(smem));
       const uint32_t bars_a = smem_a + STAGES * STAGE;
       const uint32_t full_a = bars_a, empty_a = bars_a + 8 * STAGES;
@@ -221,7 +220,7 @@ gemm2_f16_top16_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_co
             mbar_wait_warp_a(empty_a + 8 * sg, phase ^ 1);
             const uint32_t st = smem_a + sg * STAGE;
             const int k0 = (int)warp_uniform((uint32_t)(kit * D1_BK));
-            if (issuer) {
+            if (elect_one()) {
               if (leader) mbar_arrive_expect_tx_a(full_a + 8 * sg, 2 * STAGE);   // bytes of BOTH CTAs; the peer only loads
               tma_load_2d_2sm_a(st, &tm_a, full_c + 8 * sg, k0, row0);
 #pragma unroll
@@ -235,10 +234,9 @@ gemm2_f16_top16_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_co
       }
     }
   } else if (warp == 1) {
-    // whole warp in convergent code, lane 0 issues, ring position / bases warp-uniform: every tcgen05 operand lives in a
+    // whole warp in convergent code, one elected lane issues, ring position / bases warp-uniform: every tcgen05 operand lives in a
     // uniform register (tc_conv.cu, MMA issuer)
     if (warp_uniform(leader ? 1u : 0u)) {
-      const bool issuer = lane == 0;
       constexpr uint32_t idesc = umma_idesc_f16_f32(256, D1_BN);
       const uint32_t tmem_u = warp_uniform(tmem_base);
       const uint32_t smem_a = warp_uniform(smem_u32(smem));
@@ -261,7 +259,7 @@ gemm2_f16_top16_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_co
             mbar_wait_warp_a(full_a + 8 * st, phase);
             tc_fence_after();
             const uint32_t sa = smem_a + st * STAGE;
-            if (issuer) {
+            if (elect_one()) {
               const uint64_t a = umma_desc_kmajor_sw128(sa);
 #pragma unroll
               for (int k = 0; k < D1_BK / 16; ++k) {
@@ -273,12 +271,11 @@ gemm2_f16_top16_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_co
                 }
               }
               umma_commit_2sm_mc_a(empty_a + 8 * st, 0x3);
+              if (kit == kiters - 1) umma_commit_2sm_mc_a(tfull_a + 8 * as, 0x3);   // same elected thread as the MMAs
             }
             __syncwarp();
             if (++stage == STAGES) { stage = 0; phase ^= 1; }
           }
-          if (issuer) umma_commit_2sm_mc_a(tfull_a + 8 * as, 0x3);
-          __syncwarp();
         }
       }
     }

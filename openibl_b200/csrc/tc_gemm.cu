@@ -146,9 +146,8 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tm_ahi, const __grid_constant
       }
     }
   } else if (warp == 1) {
-    // MMA issuer: convergent warp, lane 0 issues, ring position and bases warp-uniform (tc_conv.cu explains why)
+    // MMA issuer: convergent warp, one elected lane issues, ring position and bases warp-uniform (tc_conv.cu explains why)
     {
-      const bool issuer = lane == 0;
       constexpr uint32_t idesc = umma_idesc_bf16_f32(GT_BM, BN);
       const uint32_t tmem_u = warp_uniform(tmem_base);
       const uint32_t smem_a = warp_uniform(smem_u32(smem));
@@ -172,7 +171,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tm_ahi, const __grid_constant
             mbar_wait_warp_a(full_a + 8 * sg, phase);
             tc_fence_after();
             const uint32_t sa = smem_a + sg * STAGE_BYTES;
-            if (issuer) {
+            if (elect_one()) {
               const uint64_t a_hi = umma_desc_kmajor<BK>(sa);
               const uint64_t a_lo = umma_desc_kmajor<BK>(sa + A_BYTES);
               const uint64_t b_hi = umma_desc_kmajor<BK>(sa + 2 * A_BYTES);
@@ -186,12 +185,11 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tm_ahi, const __grid_constant
               }
               if (MC) umma_commit_mc_a(empty_a + 8 * sg, 0x3);   // frees the slot in both CTAs of the pair
               else umma_commit_a(empty_a + 8 * sg);
+              if (kit == kn - 1) umma_commit_a(tfull_a + 8 * as);   // same elected thread as the MMAs it covers
             }
             __syncwarp();
             if (++stage == STAGES) { stage = 0; phase ^= 1; }
           }
-          if (issuer) umma_commit_a(tfull_a + 8 * as);
-          __syncwarp();
         }
       }
     }

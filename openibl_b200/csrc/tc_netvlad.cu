@@ -328,9 +328,8 @@ netvlad_tc_kernel(const __grid_constant__ CUtensorMap tm_xhi, const __grid_const
   const int n_units = a.B * a.G;
 
   if (warp == 0) {
-    // TMA producer: same discipline as the MMA issuer below (convergent warp, lane 0 issues, warp-uniform operands)
+    // TMA producer: same discipline as the MMA issuer below (convergent warp, one elected lane issues, warp-uniform operands)
     {
-      const bool issuer = lane == 0;
       const uint32_t smem_a = warp_uniform(smem_u32(smem));
       const uint32_t bars_a = smem_a + NV_NSTAGE * NV_STAGE + 2 * NV_SLOT;
       const uint32_t full_a = bars_a, empty_a = bars_a + 24;
@@ -348,7 +347,7 @@ netvlad_tc_kernel(const __grid_constant__ CUtensorMap tm_xhi, const __grid_const
             const uint32_t sg = warp_uniform((uint32_t)stage);
             mbar_wait_warp_a(empty_a + 8 * sg, phase ^ 1);
             const uint32_t st = smem_a + sg * NV_STAGE, fb = full_a + 8 * sg;
-            if (issuer) {
+            if (elect_one()) {
               mbar_arrive_expect_tx_a(fb, 3 * NV_SLOT);
               tma_load_3d_a(st, &tm_xhi, fb, c * 64, p0, b);
               tma_load_3d_a(st + NV_SLOT, &tm_xlo, fb, c * 64, p0, b);
@@ -363,7 +362,7 @@ netvlad_tc_kernel(const __grid_constant__ CUtensorMap tm_xhi, const __grid_const
           if (c1.valid()) {                       // rolling L2 prefetch: the NEXT tile's boxes, behind this tile's
             const int bn = (int)warp_uniform((uint32_t)(c1.u / a.G));   // loads (prefetching the whole unit up front
             const int pn = (int)warp_uniform((uint32_t)(c1.t * 128));   // delayed the first logits of every CTA to 10 us)
-            if (issuer) {
+            if (elect_one()) {
               for (int c2i = 0; c2i < 8; ++c2i) {
                 tma_prefetch_3d(&tm_xhi, c2i * 64, pn, bn);
                 tma_prefetch_3d(&tm_xlo, c2i * 64, pn, bn);
@@ -378,7 +377,7 @@ netvlad_tc_kernel(const __grid_constant__ CUtensorMap tm_xhi, const __grid_const
             const uint32_t sg = warp_uniform((uint32_t)stage);
             mbar_wait_warp_a(empty_a + 8 * sg, phase ^ 1);
             const uint32_t st = smem_a + sg * NV_STAGE, fb = full_a + 8 * sg;
-            if (issuer) {
+            if (elect_one()) {
               mbar_arrive_expect_tx_a(fb, 4 * NV_SLOT);
               tma_load_3d_a(st, &tm_xhi, fb, cb * 128, p0, b);
               tma_load_3d_a(st + NV_SLOT, &tm_xhi, fb, cb * 128 + 64, p0, b);
@@ -394,13 +393,12 @@ netvlad_tc_kernel(const __grid_constant__ CUtensorMap tm_xhi, const __grid_const
       }
     }
   } else if (warp == 1) {
-    // MMA issuer: the whole warp walks the schedule in convergent code, lane 0 issues; ring position and bases pass
+    // MMA issuer: the whole warp walks the schedule in convergent code, ONE ELECTED lane issues; ring position and bases pass
     // through warp_uniform() so that every tcgen05 operand lives in a uniform register.  Inside an `if (lane == 0)`
     // region each of the 160 small MMAs of a tile (N = 64 / 128: 32-65 clk of tensor pipe) was wrapped in an ELECT +
     // R2UR.BROADCAST loop of ~90-100 clk -- round 1's "3.5 us + 4.7 us per tile" were ISSUE time, not shared-memory
     // bandwidth.
     {
-      const bool issuer = lane == 0;
       constexpr uint32_t idesc_n128 = umma_idesc_bf16_f32(128, 128);
       constexpr uint32_t idesc_n64 = umma_idesc_bf16_f32(128, 64);
       constexpr uint32_t idesc2 = umma_idesc_bf16_f32_mn(128, 64, 1, 1);
@@ -428,7 +426,7 @@ netvlad_tc_kernel(const __grid_constant__ CUtensorMap tm_xhi, const __grid_const
             mbar_wait_warp_a(full_a + 8 * st, phase);
             tc_fence_after();
             const uint32_t sa = smem_a + st * NV_STAGE;
-            if (issuer) {
+            if (elect_one()) {
               const uint64_t xh = umma_desc_kmajor_sw128(sa), xl = umma_desc_kmajor_sw128(sa + NV_SLOT);
               const uint64_t wcat = umma_desc_kmajor_sw128(sa + 2 * NV_SLOT);   // 128 rows: W_hi then W_lo
 #pragma unroll
@@ -438,18 +436,17 @@ netvlad_tc_kernel(const __grid_constant__ CUtensorMap tm_xhi, const __grid_const
                 umma_bf16(t_z, xl + ko, wcat + ko, idesc_n64, 1u);               // x_lo . W_hi into columns 0-63
               }
               umma_commit_a(empty_a + 8 * st);
+              if (c == 7) umma_commit_a(zfull_a + 8 * zb);   // same elected thread as the MMAs it covers
             }
             __syncwarp();
             if (++stage == NV_NSTAGE) { stage = 0; phase ^= 1; }
           }
-          if (issuer) umma_commit_a(zfull_a + 8 * zb);
-          __syncwarp();
           c1.next();
           ++n1;
         }
         if (n2 < n1 - 1 || !c1.valid()) {
           // ---- GEMM 2 of tile n2: V[128 c, 64 k] (4 channel blocks) += X^T a' ----
-          const bool fresh = c2.first();
+          const bool fresh = c2.first(), unit_done = c2.last();
           if (fresh) {
             mbar_wait_warp_a(dempty_a, (c2.useq & 1) ^ 1);   // the previous unit's partial has been read out of TMEM
             tc_fence_after();
@@ -462,7 +459,7 @@ netvlad_tc_kernel(const __grid_constant__ CUtensorMap tm_xhi, const __grid_const
             tc_fence_after();
             const uint32_t sa = smem_a + st * NV_STAGE;
             const uint32_t d = t_du + warp_uniform((uint32_t)cb) * 64;
-            if (issuer) {
+            if (elect_one()) {
 #pragma unroll
               for (int ks = 0; ks < 8; ++ks) {     // 16 pixel rows (2048 B) per MMA
                 const uint32_t off = ks * 2048;
@@ -475,15 +472,14 @@ netvlad_tc_kernel(const __grid_constant__ CUtensorMap tm_xhi, const __grid_const
                 umma_bf16(d, xh, bh, idesc2, 1u);
               }
               umma_commit_a(empty_a + 8 * st);
+              if (cb == 3) {
+                umma_commit_a(aempty_a);             // a' may be overwritten
+                if (unit_done) umma_commit_a(dfull_a);
+              }
             }
             __syncwarp();
             if (++stage == NV_NSTAGE) { stage = 0; phase ^= 1; }
           }
-          if (issuer) {
-            umma_commit_a(aempty_a);               // a' may be overwritten
-            if (c2.last()) umma_commit_a(dfull_a);
-          }
-          __syncwarp();
           c2.next();
           ++n2;
         }
