@@ -117,29 +117,39 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tm_ahi, const __grid_constant
   };
 
   if (warp == 0) {
-    if (lane == 0) {
+    // TMA producer: convergent warp, one elected lane issues, warp-uniform operands (tc_conv.cu explains why)
+    {
+      const uint32_t smem_a = warp_uniform(smem_u32(smem));
+      const uint32_t bars_a = smem_a + STAGES * STAGE_BYTES;
+      const uint32_t full_a = bars_a, empty_a = bars_a + 8 * STAGES;
+      const int rank_u = (int)warp_uniform(cta_rank);
       int stage = 0;
       uint32_t phase = 0;
       for (int item = unit0; item < g.total_items; item += unit_stride) {
         int mt, nt0, ntn, k0, kn;
         decode(item, mt, nt0, ntn, k0, kn);
+        const int row0 = (int)warp_uniform((uint32_t)(mt * GT_BM));
         for (int nt = nt0; nt < nt0 + ntn; ++nt) {
+          const int col0 = (int)warp_uniform((uint32_t)(nt * BN));
           for (int kit = k0; kit < k0 + kn; ++kit) {
-            mbar_wait(&empty_bar[stage], phase ^ 1);
-            uint8_t* st = smem + stage * STAGE_BYTES;
-            mbar_arrive_expect_tx(&full_bar[stage], STAGE_BYTES);
-            tma_load_2d(st, &tm_ahi, &full_bar[stage], kit * BK, mt * GT_BM);
-            tma_load_2d(st + A_BYTES, &tm_alo, &full_bar[stage], kit * BK, mt * GT_BM);
-            if (MC) {   // this CTA's half of the B tile, delivered to both CTAs of the pair
-              constexpr int HB = B_BYTES / 2;
-              tma_load_2d_mc(st + 2 * A_BYTES + cta_rank * HB, &tm_bhi, &full_bar[stage], kit * BK,
-                             nt * BN + (int)cta_rank * (BN / 2), 0x3);
-              tma_load_2d_mc(st + 2 * A_BYTES + B_BYTES + cta_rank * HB, &tm_blo, &full_bar[stage],
-                             kit * BK, nt * BN + (int)cta_rank * (BN / 2), 0x3);
-            } else {
-              tma_load_2d(st + 2 * A_BYTES, &tm_bhi, &full_bar[stage], kit * BK, nt * BN);
-              tma_load_2d(st + 2 * A_BYTES + B_BYTES, &tm_blo, &full_bar[stage], kit * BK, nt * BN);
+            const uint32_t sg = warp_uniform((uint32_t)stage);
+            mbar_wait_warp_a(empty_a + 8 * sg, phase ^ 1);
+            const uint32_t st = smem_a + sg * STAGE_BYTES, fb = full_a + 8 * sg;
+            const int kc = (int)warp_uniform((uint32_t)(kit * BK));
+            if (elect_one()) {
+              mbar_arrive_expect_tx_a(fb, STAGE_BYTES);
+              tma_load_2d_a(st, &tm_ahi, fb, kc, row0);
+              tma_load_2d_a(st + A_BYTES, &tm_alo, fb, kc, row0);
+              if (MC) {   // this CTA's half of the B tile, delivered to both CTAs of the pair
+                constexpr int HB = B_BYTES / 2;
+                tma_load_2d_mc_a(st + 2 * A_BYTES + rank_u * HB, &tm_bhi, fb, kc, col0 + rank_u * (BN / 2), 0x3);
+                tma_load_2d_mc_a(st + 2 * A_BYTES + B_BYTES + rank_u * HB, &tm_blo, fb, kc, col0 + rank_u * (BN / 2), 0x3);
+              } else {
+                tma_load_2d_a(st + 2 * A_BYTES, &tm_bhi, fb, kc, col0);
+                tma_load_2d_a(st + 2 * A_BYTES + B_BYTES, &tm_blo, fb, kc, col0);
+              }
             }
+            __syncwarp();
             if (++stage == STAGES) { stage = 0; phase ^= 1; }
           }
         }

@@ -78,61 +78,77 @@ gemm2_top16_kernel(const __grid_constant__ CUtensorMap tm_ahi, const __grid_cons
   };
   const int kiters = g.K / G2_BK;
 
+  // Producer and MMA issuer: convergent warps, one elected lane issues a stage's TMA / tcgen05 instructions, ring
+  // position and bases warp-uniform (tc_conv.cu, MMA issuer, explains what `if (lane == 0)` costs per instruction).
   if (warp == 0) {
-    if (lane == 0) {
-      int stage = 0; uint32_t phase = 0;
-      for (int item = unit0; item < g.total_items; item += unit_stride) {
-        int mp, nt0, ntn;
-        decode(item, mp, nt0, ntn);
-        const int row0 = (mp * 2 + (int)rank) * 128;
-        for (int nt = nt0; nt < nt0 + ntn; ++nt) {
-          const int col0 = nt * G2_BN + (int)rank * (G2_BN / 2);
-          for (int kit = 0; kit < kiters; ++kit) {
-            mbar_wait(&empty_bar[stage], phase ^ 1);
-            uint8_t* st = smem + stage * G2_STAGE;
-            const uint32_t lead_full = mapa_u32(smem_u32(&full_bar[stage]), 0);
-            if (leader) mbar_arrive_expect_tx(&full_bar[stage], 2 * G2_STAGE);   // bytes of BOTH CTAs; the peer only loads
-            tma_load_2d_2sm(st, &tm_ahi, lead_full, kit * G2_BK, row0);
-            tma_load_2d_2sm(st + G2_A_BYTES, &tm_alo, lead_full, kit * G2_BK, row0);
-            tma_load_2d_2sm(st + 2 * G2_A_BYTES, &tm_bhi, lead_full, kit * G2_BK, col0);
-            tma_load_2d_2sm(st + 2 * G2_A_BYTES + G2_BH_BYTES, &tm_blo, lead_full, kit * G2_BK, col0);
-            if (++stage == G2_STAGES) { stage = 0; phase ^= 1; }
+    const uint32_t smem_a = warp_uniform(smem_u32(smem));
+    const uint32_t full_a = smem_a + G2_STAGES * G2_STAGE, empty_a = full_a + 8 * G2_STAGES;
+    const uint32_t full_c = warp_uniform(mapa_u32(full_a, 0));   // the leader's barriers, shared::cluster addresses
+    const int rank_u = (int)warp_uniform(rank);
+    int stage = 0; uint32_t phase = 0;
+    for (int item = unit0; item < g.total_items; item += unit_stride) {
+      int mp, nt0, ntn;
+      decode(item, mp, nt0, ntn);
+      const int row0 = (int)warp_uniform((uint32_t)((mp * 2 + rank_u) * 128));
+      for (int nt = nt0; nt < nt0 + ntn; ++nt) {
+        const int col0 = (int)warp_uniform((uint32_t)(nt * G2_BN + rank_u * (G2_BN / 2)));
+        for (int kit = 0; kit < kiters; ++kit) {
+          const uint32_t sg = warp_uniform((uint32_t)stage);
+          mbar_wait_warp_a(empty_a + 8 * sg, phase ^ 1);
+          const uint32_t st = smem_a + sg * G2_STAGE, fb = full_c + 8 * sg;
+          const int k0 = (int)warp_uniform((uint32_t)(kit * G2_BK));
+          if (elect_one()) {
+            if (leader) mbar_arrive_expect_tx_a(full_a + 8 * sg, 2 * G2_STAGE);   // bytes of BOTH CTAs; the peer only loads
+            tma_load_2d_2sm_a(st, &tm_ahi, fb, k0, row0);
+            tma_load_2d_2sm_a(st + G2_A_BYTES, &tm_alo, fb, k0, row0);
+            tma_load_2d_2sm_a(st + 2 * G2_A_BYTES, &tm_bhi, fb, k0, col0);
+            tma_load_2d_2sm_a(st + 2 * G2_A_BYTES + G2_BH_BYTES, &tm_blo, fb, k0, col0);
           }
+          __syncwarp();
+          if (++stage == G2_STAGES) { stage = 0; phase ^= 1; }
         }
       }
     }
   } else if (warp == 1) {
-    if (leader && lane == 0) {
+    if (warp_uniform(leader ? 1u : 0u)) {
       constexpr uint32_t idesc = umma_idesc_bf16_f32(256, G2_BN);
+      const uint32_t tmem_u = warp_uniform(tmem_base);
+      const uint32_t smem_a = warp_uniform(smem_u32(smem));
+      const uint32_t full_a = smem_a + G2_STAGES * G2_STAGE, empty_a = full_a + 8 * G2_STAGES;
+      const uint32_t tfull_a = full_a + 16 * G2_STAGES, tempty_a = tfull_a + 16;
       int stage = 0; uint32_t phase = 0;
       int it = 0;
       for (int item = unit0; item < g.total_items; item += unit_stride) {
         int mp, nt0, ntn;
         decode(item, mp, nt0, ntn);
         for (int nt = nt0; nt < nt0 + ntn; ++nt, ++it) {
-          const int as = it & 1;
+          const uint32_t as = warp_uniform((uint32_t)(it & 1));
           const uint32_t aphase = (it >> 1) & 1;
-          mbar_wait(&tempty_bar[as], aphase ^ 1);
+          mbar_wait_warp_a(tempty_a + 8 * as, aphase ^ 1);
           tc_fence_after();
-          const uint32_t d_tmem = tmem_base + as * G2_BN;
+          const uint32_t d_tmem = tmem_u + as * G2_BN;
           for (int kit = 0; kit < kiters; ++kit) {
-            mbar_wait(&full_bar[stage], phase);
+            const uint32_t sg = warp_uniform((uint32_t)stage);
+            mbar_wait_warp_a(full_a + 8 * sg, phase);
             tc_fence_after();
-            const uint32_t sa = smem_u32(smem + stage * G2_STAGE);
-            const uint64_t a_hi = umma_desc_kmajor_sw128(sa), a_lo = umma_desc_kmajor_sw128(sa + G2_A_BYTES);
-            const uint64_t b_hi = umma_desc_kmajor_sw128(sa + 2 * G2_A_BYTES);
-            const uint64_t b_lo = umma_desc_kmajor_sw128(sa + 2 * G2_A_BYTES + G2_BH_BYTES);
+            const uint32_t sa = smem_a + sg * G2_STAGE;
+            if (elect_one()) {
+              const uint64_t a_hi = umma_desc_kmajor_sw128(sa), a_lo = umma_desc_kmajor_sw128(sa + G2_A_BYTES);
+              const uint64_t b_hi = umma_desc_kmajor_sw128(sa + 2 * G2_A_BYTES);
+              const uint64_t b_lo = umma_desc_kmajor_sw128(sa + 2 * G2_A_BYTES + G2_BH_BYTES);
 #pragma unroll
-            for (int k = 0; k < G2_BK / 16; ++k) {
-              const uint64_t ko = (uint64_t)(k * 2);
-              umma_bf16_2sm(d_tmem, a_lo + ko, b_hi + ko, idesc, (kit > 0 || k > 0) ? 1u : 0u);
-              umma_bf16_2sm(d_tmem, a_hi + ko, b_lo + ko, idesc, 1u);
-              umma_bf16_2sm(d_tmem, a_hi + ko, b_hi + ko, idesc, 1u);
+              for (int k = 0; k < G2_BK / 16; ++k) {
+                const uint64_t ko = (uint64_t)(k * 2);
+                umma_bf16_2sm(d_tmem, a_lo + ko, b_hi + ko, idesc, (kit > 0 || k > 0) ? 1u : 0u);
+                umma_bf16_2sm(d_tmem, a_hi + ko, b_lo + ko, idesc, 1u);
+                umma_bf16_2sm(d_tmem, a_hi + ko, b_hi + ko, idesc, 1u);
+              }
+              umma_commit_2sm_mc_a(empty_a + 8 * sg, 0x3);
+              if (kit == kiters - 1) umma_commit_2sm_mc_a(tfull_a + 8 * as, 0x3);   // same elected thread as the MMAs
             }
-            umma_commit_2sm_mc(&empty_bar[stage], 0x3);
+            __syncwarp();
             if (++stage == G2_STAGES) { stage = 0; phase ^= 1; }
           }
-          umma_commit_2sm_mc(&tfull_bar[as], 0x3);
         }
       }
     }

@@ -26,8 +26,10 @@ import torch.distributed as dist
 from .evaluators import recalls_from_topk, sharded_topk, _all_gather_rows
 from .utils.data.sampler import slice_bounds
 
+import os
+
 SEED_DB, SEED_Q, SEED_POS = 1_000_003, 7_000_003, 12345
-NOISE, AMP = 0.5, 2.0
+NOISE, AMP = float(os.environ.get("IBL_GALLERY_NOISE", 0.5)), 2.0
 
 
 def planted_positives(n_db: int, n_q: int) -> np.ndarray:
@@ -54,6 +56,26 @@ def make_image_batch(kind: str, first: int, count: int, H: int, W: int, dev, pos
             g.manual_seed(SEED_Q + i)
             x[j].add_(torch.randn(3, H, W, device=dev, generator=g), alpha=NOISE)
     return x[:count]
+
+
+def center_pca(eng, weight: torch.Tensor, H: int, W: int, batch: int, n_sample: int = 256) -> torch.Tensor:
+    """Sets the PCA layer's bias to -W.mean, mean = the mean VLAD descriptor of the first `n_sample` database images
+    -- what a PCA FIT does (ibl/pca.py:30-33, 86-90 centre the training descriptors; the reference's Conv2d bias is
+    -W.mean), without which a random-init trunk's descriptors all point the same way (pairwise distances ~1e-5, the
+    ranking then decided by the noise of whatever arithmetic computes them).  Every rank runs this on the SAME images,
+    and extraction is batch-invariant, so all ranks set bit-identical parameters.  Returns the bias it set."""
+    dev = torch.device("cuda", eng.device)
+    acc = None
+    buf = torch.empty(batch, 3, H, W, device=dev)
+    for b0 in range(0, n_sample, batch):
+        nb = min(batch, n_sample - b0)
+        v, _ = eng.extract(make_image_batch("db", b0, nb, H, W, dev, out=buf), pca=False)
+        acc = v.double().sum(0) if acc is None else acc + v.double().sum(0)
+    mean = acc / n_sample
+    w2 = weight.detach().reshape(weight.shape[0], -1).to(dev)
+    bias = (-(w2.double() @ mean)).float().contiguous()
+    eng.set_pca(weight, bias, force=True)
+    return bias
 
 
 def extract_slice(eng, kind: str, n_total: int, world: int, rank: int, H: int, W: int, batch: int, dev, pos=None,
