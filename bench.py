@@ -460,9 +460,14 @@ def main():
         if proj > args.strong_budget_s:
             strong = {"skipped": f"projected extraction time {proj:.0f} s exceeds --strong-budget-s {args.strong_budget_s:.0f}"}
         else:
+            # PCA bias = -W.mean of a database sample, as a PCA fit sets it (ibl/pca.py:86-90): without the centring a
+            # random-init trunk's descriptors are ~1e-5 apart and the ranking is decided by rounding noise
+            gallery.center_pca(eng, sd["pca_layer.weight"], H, W, BATCH)
             # warm-up outside the timed region: allocations, NCCL communicator and its first-call setup
             gallery.run(eng, 2 * BATCH * world, 64, H, W, BATCH, check_exact=False)
             strong = gallery.run(eng, args.strong_db, NQ, H, W, BATCH, check_exact=False)
+            strong["guard_flagged_queries_rank0"] = eng.dist_flagged()
+            eng.set_pca(sd["pca_layer.weight"], sd["pca_layer.bias"], force=True)
             strong["note"] = ("same 250k-image gallery whatever N (images seeded by global index): topk_index_hash and "
                               "recalls must be equal across N; total_s is the strong-scaling time (max over ranks)")
 

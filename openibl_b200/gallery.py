@@ -4,8 +4,12 @@ Shared by bench.py (`strong_250k`), tools/bench_gallery.py and tests/test_gpu_e2
 
 Every image is generated on the device from a seed that depends only on its GLOBAL index, so the gallery --
 and therefore every descriptor, every distance and the final ranking -- is the same whatever the world
-size.  Query j is a noisy copy of database image pos[j] (so Recall@N is a real, non-trivial number); images are smooth
-random fields, not white noise, so that descriptors of different images are 2e-2..7e-2 apart.
+size.  Query j is a noisy copy of database image pos[j] (so Recall@N is a real number); images are smooth random
+fields, not white noise.  A random-init trunk still maps all of them to almost the same descriptor (pairwise distances
+~1e-5: measured, profiles/r02_diag_gallery.jsonl -- every query then trips the screening guard and even fp32 "exact"
+distances are rounding noise), so callers that want a meaningful ranking first centre the PCA layer on a database sample
+(center_pca below: what a PCA fit does); distances are then ~0.8 and Recall@1 goes from 0.999 (query noise 0.1 sigma) to
+~0 (0.5 sigma) on 30k images; the default noise is 0.2 sigma.
 
 Flow (reference: ibl/evaluators.py:76-101,105-130,142-167 is what it replaces):
   1. rank r extracts its DistributedSliceSampler slice of the database and of the queries
@@ -29,7 +33,7 @@ from .utils.data.sampler import slice_bounds
 import os
 
 SEED_DB, SEED_Q, SEED_POS = 1_000_003, 7_000_003, 12345
-NOISE, AMP = float(os.environ.get("IBL_GALLERY_NOISE", 0.5)), 2.0
+NOISE, AMP = float(os.environ.get("IBL_GALLERY_NOISE", 0.2)), 2.0
 
 
 def planted_positives(n_db: int, n_q: int) -> np.ndarray:
@@ -42,7 +46,7 @@ def make_image_batch(kind: str, first: int, count: int, H: int, W: int, dev, pos
     A database image is a smooth random field (a 3 x H/16 x W/16 normal sample, seeded by the image's global index,
     bilinearly upsampled and scaled by 2): white noise would give every image almost the same descriptor through a
     random-init trunk (all pairwise distances ~1e-6), smooth structure gives distances of 2e-2..7e-2.  Query j is the
-    field of database image pos[j] plus 0.5-sigma white noise seeded by j."""
+    field of database image pos[j] plus NOISE-sigma white noise seeded by j."""
     x = out if out is not None else torch.empty(count, 3, H, W, device=dev)
     g = torch.Generator(device=dev)
     ch, cw = max(H // 16, 2), max(W // 16, 2)
