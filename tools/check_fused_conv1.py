@@ -1,6 +1,6 @@
 #!/usr/bin/env python
 """Quick GPU check of the fused conv1_1+conv1_2 kernel against the two separate kernels (run in two processes by
-tools/gpu_session3.sh: the env switch is read once per process).  Prints a checksum line; `--time` also times it."""
+tools/sessions/gpu_session3b.sh: the env switch is read once per process).  Prints a checksum line; `--time` also times it."""
 import sys, os
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 import ctypes
