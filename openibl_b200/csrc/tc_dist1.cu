@@ -707,7 +707,7 @@ int launch_dist_topk_1pass(const float* q, int m, const float* db, int n, int n_
     IBL_RET(make_tmap(&ma, CU_TENSOR_MAP_DATA_TYPE_FLOAT16, 2, qp, dims_a, str, box));
     IBL_RET(make_tmap(&mb, CU_TENSOR_MAP_DATA_TYPE_FLOAT16, 2, dp, dims_b, str, box));
   }
-  // IBL_DIST_BN=256 selects the 256 x 256 tile with two overlapped accumulators (A/B measurements, variant tests)
+  // default: 256 x 256 tiles with two overlapped accumulators; IBL_DIST_BN=512 selects the 256 x 512 tile (variant tests)
   static const int tile_env = [] { const char* v = getenv("IBL_DIST_BN"); return v ? atoi(v) : 256; }();
   const int SUBn = tile_env == 256 ? 1 : 2;
   Dist1Args g{};

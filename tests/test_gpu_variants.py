@@ -17,7 +17,7 @@ VARIANTS = [
     ({"IBL_CONV_2SM": "2", "IBL_CONV_HALO": "0"}, "conv3x3 or odd"),        # SM pairs on the 128-wide tiles too
     ({"IBL_CONV1_FUSED": "0"}, "small or odd or hub or tokyo"),             # separate conv1_1 / conv1_2 kernels
     ({"IBL_CONV1_FUSED": "0", "IBL_CONV1_SIMT": "1"}, "small or odd"),      # ... with the CUDA-core conv1_1
-    ({"IBL_DIST_BN": "256"}, "retrieval or topk or single_pass"),            # 256 x 256 screening tiles, two accumulators
+    ({"IBL_DIST_BN": "512"}, "retrieval or topk or single_pass"),            # 256 x 512 screening tiles, one accumulator
     ({"IBL_DIST_SCREEN": "3"}, "retrieval or topk"),                         # round-1 bf16x3 screening on SM pairs
     ({"IBL_DIST_SCREEN": "3", "IBL_DIST_2SM": "0"}, "retrieval_vs_reference or topk"),   # ... on one SM
     ({"IBL_DIST_SCREEN": "3", "IBL_DIST_2SM": "0", "IBL_DIST_BN": "128", "IBL_GEMM_MC": "1"}, "retrieval_vs_reference or topk"),
