@@ -87,6 +87,12 @@ def load_conv_traffic():
     if not os.path.exists(p):
         return {"dram_bytes_per_step": None, "note": "no ncu traffic table committed (profiles/r02_conv_traffic.json)"}
     t = json.load(open(p))
+    if os.environ.get("IBL_CONV1_FUSED", "1") != "0" and "dram_bytes_total_with_fused_conv1" in t:
+        return {"dram_bytes_per_step": t["dram_bytes_total_with_fused_conv1"],
+                "vs_algorithmic": t.get("vs_algorithmic_with_fused_conv1"),
+                "note": "conv1_fused_tc_kernel (its own ncu --set full capture, profiles/r02_conv1_fused.md) + the 11 "
+                        "conv3x3_tc_kernel launches conv2_1..conv5_3 of one batch-32 step (per-layer table "
+                        f"profiles/r02_conv_traffic.json / .md, {t.get('captured', 'ncu')}): ncu dram read+write"}
     return {"dram_bytes_per_step": t["dram_bytes_total"], "vs_algorithmic": t.get("vs_algorithmic"),
             "note": f"sum over the 12 conv3x3_tc_kernel launches of one step, ncu dram read+write, per-layer table in "
                     f"profiles/r02_conv_traffic.json / .md ({t.get('captured', 'ncu')})"}
