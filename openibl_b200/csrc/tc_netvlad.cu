@@ -396,8 +396,8 @@ netvlad_tc_kernel(const __grid_constant__ CUtensorMap tm_xhi, const __grid_const
     // MMA issuer: the whole warp walks the schedule in convergent code, ONE ELECTED lane issues; ring position and bases pass
     // through warp_uniform() so that every tcgen05 operand lives in a uniform register.  Inside an `if (lane == 0)`
     // region each of the 160 small MMAs of a tile (N = 64 / 128: 32-65 clk of tensor pipe) was wrapped in an ELECT +
-    // R2UR.BROADCAST loop of ~90-100 clk -- round 1's "3.5 us + 4.7 us per tile" were ISSUE time, not shared-memory
-    // bandwidth.
+    // R2UR.BROADCAST loop of ~90-100 clk -- a good part of round 1's "3.5 us + 4.7 us per tile" was ISSUE time, not
+    // shared-memory bandwidth (66.6 -> 62.2 us for the kernel with elected-lane issue).
     {
       constexpr uint32_t idesc_n128 = umma_idesc_bf16_f32(128, 128);
       constexpr uint32_t idesc_n64 = umma_idesc_bf16_f32(128, 64);
