@@ -310,3 +310,73 @@ def test_tuple_samplers_yield_reference_tuples_given_the_reference_ranking():
             for ep in (0, 1):
                 got = np.asarray([r + [-1] * (9 - len(r)) for r in iter(s)], dtype=np.int64)   # ragged rows padded with -1
                 assert np.array_equal(got, g[f"{name}_r{rank}_e{ep}"]), (name, rank, ep)
+
+
+def test_distance_screening_selection_model_keeps_the_true_top16():
+    """Model check of the selection logic of gemm2_f16_top16_kernel's epilogue (tc_dist1.cu): per work item a sorted
+    top-16, a threshold that is only refreshed at merges, a 32-slot pending list flushed when it could overflow within
+    the next 16 columns, and a per-query gate shared between concurrently running items through atomicMin with
+    arbitrarily STALE reads.  Whatever the interleaving, the union of the items' lists must contain the true 16
+    smallest screened distances of the row (the guard of dist_finish_kernel assumes exactly that)."""
+    import numpy as np
+    rng = np.random.RandomState(11)
+    PEND, TILE = 32, 256
+
+    def run_row(vals, n_items, order_seed, adversarial):
+        n = len(vals)
+        per = -(-n // (n_items * TILE)) * TILE
+        items = [dict(lo=i * per, hi=min(n, (i + 1) * per), pos=i * per, td=[np.inf] * 16, ti=[-1] * 16, thr=np.inf,
+                      pend=[]) for i in range(n_items)]
+        gate_hist = [np.inf]                                  # every value the gate ever had: a reader may see any of them
+        sched = np.random.RandomState(order_seed)
+
+        def merge(it):
+            for d, c in it["pend"]:
+                if d < it["td"][15]:
+                    p = sum(1 for t in it["td"] if t <= d)
+                    it["td"].insert(p, d); it["ti"].insert(p, c)
+                    it["td"].pop(); it["ti"].pop()
+            it["pend"] = []
+
+        live = [it for it in items if it["pos"] < it["hi"]]
+        while live:
+            it = live[sched.randint(len(live))]
+            seen = gate_hist[sched.randint(len(gate_hist))] if adversarial else gate_hist[-1]
+            it["thr"] = min(it["thr"], seen)                  # stale or fresh gate read at the start of a tile
+            end = min(it["hi"], it["pos"] + TILE)
+            for g0 in range(it["pos"], end, 16):
+                if len(it["pend"]) > PEND - 16:
+                    merge(it)
+                    it["thr"] = min(it["thr"], it["td"][15])
+                for c in range(g0, min(end, g0 + 16)):
+                    if vals[c] < it["thr"]:
+                        it["pend"].append((vals[c], c))
+                assert len(it["pend"]) <= PEND
+            merge(it)
+            if it["td"][15] < it["thr"]:
+                it["thr"] = it["td"][15]
+                gate_hist.append(min(gate_hist[-1], it["thr"]))
+            it["pos"] = end
+            live = [x for x in items if x["pos"] < x["hi"]]
+        got = sorted(d for it in items for d in it["td"] if np.isfinite(d))[:16]
+        return np.array(got)
+
+    for trial in range(40):
+        n = int(rng.choice([300, 1000, 4096, 10000]))
+        kind = trial % 4
+        if kind == 0:
+            vals = rng.rand(n)
+        elif kind == 1:
+            vals = np.sort(rng.rand(n))[::-1].copy()          # descending: every column beats the running 16th best
+        elif kind == 2:
+            vals = np.round(rng.rand(n), 2)                   # heavy ties, also at the threshold
+        else:
+            vals = np.abs(rng.randn(n)) * (1 + (np.arange(n) % 7 == 0) * -0.9)
+        vals = vals.astype(np.float32)
+        want = np.sort(vals)[:16]
+        for n_items in (1, 3, 8):
+            got = run_row(vals, n_items, order_seed=trial * 10 + n_items, adversarial=True)
+            # A candidate is dropped only against a gate that is some item's 16th best, i.e. that item holds 16 values
+            # <= the gate -- so every dropped value is >= the merged 16th best and the merged VALUES are exactly the 16
+            # smallest (with ties at the 16th place, which copy survives is arbitrary; the indices are not compared).
+            assert np.array_equal(got, want[: len(got)]) and len(got) == min(16, n), (trial, n_items, got, want)
